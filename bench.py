@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: warp+loss fwd/bwd Mpixel/s and
+HBM GB/s vs peak) on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c5|c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the fused op over one batch of synthetic Cityscapes-shaped input
+(BASELINE.json configs[1]: 16x256x512, K=20, fp32): flow-guided warp of RGB + layout, all loss
+terms, gradients to flow, src_rgb and src_layout.  Weak scaling: every rank processes one such
+batch; the only exchange is one NCCL all-reduce of the 8-float loss vector.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the
+public module API from pinned host buffers, `roofline` is live CUDA-event timing of the dominant
+kernel against MEASURED_PEAKS.json, `cpu_baseline` is the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (N, H, W, K, flow sigma px, far fraction, dtype)
+    "c1": (2, 128, 256, 20, 4.0, 0.0, "f32"),
+    "c2": (16, 256, 512, 20, 4.0, 0.0, "f32"),
+    "c3": (8, 1024, 2048, 20, 4.0, 0.0, "bf16"),
+    "c5": (16, 375, 1242, 20, 48.0, 0.05, "f32"),
+}
+BYTES_PER_PX = {"f32": dict(step=220, pass1=128, pass2=92), "bf16": dict(step=122, pass1=76, pass2=46)}
+FALLBACK_HBM_GBS = 6650.0
+
+
+def make_inputs(N, H, W, K, sigma, far, dtype, device, seed=1024):
+    """Synthetic Cityscapes-shaped batch: normalised RGB, block-constant one-hot
+    layouts, block-constant int64 labels, box-smoothed Gaussian flow."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    mean = torch.tensor([0.485, 0.456, 0.406])[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225])[None, :, None, None]
+    src_rgb = (torch.rand(N, 3, H, W, generator=g) - mean) / std
+    tgt_rgb = (torch.rand(N, 3, H, W, generator=g) - mean) / std
+    blk = 32
+
+    def labels():
+        l = torch.randint(0, K, (N, (H + blk - 1) // blk, (W + blk - 1) // blk), generator=g)
+        return l.repeat_interleave(blk, 1).repeat_interleave(blk, 2)[:, :H, :W].contiguous()
+
+    lab_src, lab_tgt = labels(), labels()
+    src_layout = torch.zeros(N, K, H, W).scatter_(1, lab_src[:, None], 1.0)
+    flow = torch.randn(N, 2, H, W, generator=g) * sigma
+    flow = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(flow, (4, 4, 4, 4), mode="replicate"), 9, 1)
+    if far > 0:
+        m = torch.rand(N, 1, H, W, generator=g) < far
+        flow = torch.where(m, (torch.rand(N, 2, H, W, generator=g) - 0.5) * 2 * max(H, W), flow)
+    flow = flow.permute(0, 2, 3, 1).contiguous()
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    out = dict(src_rgb=src_rgb.to(tdt), src_layout=src_layout.to(tdt), flow=flow, tgt_rgb=tgt_rgb.to(tdt),
+               tgt_label=lab_tgt)
+    if device is not None:
+        cl = lambda t: t.to(device).contiguous(memory_format=torch.channels_last)
+        out = dict(src_rgb=cl(out["src_rgb"]), src_layout=cl(out["src_layout"]), flow=flow.to(device),
+                   tgt_rgb=cl(out["tgt_rgb"]), tgt_label=lab_tgt.to(device))
+    return out
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_throughput(N, H, W, K, sigma, far, n_sample, iters):
+    """Oracle port (torch CPU composition of the reference's losses + grid_sample) on a bounded
+    sample of the workload: fwd+bwd to flow, src_rgb, src_layout.  Returns Mpixel/s."""
+    from oracle import torch_oracle as TO
+    d = make_inputs(n_sample, H, W, K, sigma, far, "f32", None)
+    ts = []
+    for i in range(iters + 1):
+        t0 = time.perf_counter()
+        TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"], w_tv=0.5)
+        ts.append(time.perf_counter() - t0)
+    ts = sorted(ts[1:])  # first call = warm-up
+    t = ts[len(ts) // 2]
+    return n_sample * H * W / t / 1e6, t
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
+    pure Python/PyTorch with no compiled code of its own, so this is the oracle port
+    (oracle/torch_oracle.py) on the box's host cores, all threads."""
+    if rank != 0:
+        return
+    N, H, W, K, sigma, far, dtype = WORKLOADS[args.workload]
+    n_sample = min(N, 2)
+    ts = []
+    from oracle import torch_oracle as TO
+    d = make_inputs(n_sample, H, W, K, sigma, far, "f32", None)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"], w_tv=0.5)
+        if i >= args.warmup:
+            ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    val = n_sample * H * W / t / 1e6
+    sample = f"{n_sample}x{H}x{W} slice of the {N}x{H}x{W} batch per step, torch CPU oracle port, fwd+bwd"
+    print(json.dumps({
+        "impl": "reference", "metric": "warp+loss fwd/bwd throughput", "value": val, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {N}x{H}x{W} K={K} fp32 fwd+bwd (bounded sample {n_sample}x{H}x{W} per step)"},
+        "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flow-grad-only", action="store_true", help="sources are data: no d_src (128 B/px variant)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import vlg_b200
+    from vlg_b200 import _cabi
+    from vlg_b200 import ops as vops
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    N, H, W, K, sigma, far, dtype = WORKLOADS[args.workload]
+    P = N * H * W
+    with_src = not args.flow_grad_only
+    lib = _cabi.load()
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+
+    # two input sets, alternated, so no step re-reads lines its predecessor left in L2
+    sets = [make_inputs(N, H, W, K, sigma, far, dtype, dev, seed=1024 + 7 * rank + s) for s in range(2)]
+    cfg = vops.WarpLossConfig(w_tv=0.5)
+    prob = vops._problem(N, H, W, K, tdt, cfg)
+    ws = vops._workspace(prob, with_src, dev)
+    loss = torch.zeros(_cabi.LOSS_SLOTS, dtype=torch.float32, device=dev)
+    d_c = torch.empty(N, H, W, 2, dtype=torch.float32, device=dev)
+    d_a = vops.empty_nhwc((N, 3, H, W), tdt, dev) if with_src else None
+    d_b = vops.empty_nhwc((N, K, H, W), tdt, dev) if with_src else None
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    ptr = vops._ptr
+
+    def step(i, evs=None):
+        s = sets[i & 1]
+        vops.check(lib.vlg_warp_loss_bwd_out(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
+                                             ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(d_c), None, int(with_src),
+                                             ptr(ws), ws.numel(), sp))
+        if evs: evs[1].record(stream)
+        vops.check(lib.vlg_reduce_partials(C.byref(prob), ptr(loss), ptr(ws), ws.numel(), sp))
+        if evs: evs[2].record(stream)
+        if with_src:
+            vops.check(lib.vlg_warp_bwd_src(C.byref(prob), ptr(s["flow"]), ptr(d_a), ptr(d_b), ptr(ws), ws.numel(), sp))
+        if dist is not None:
+            dist.all_reduce(loss)          # the path's only exchange: one 8-float loss vector
+        if evs: evs[3].record(stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed region 1: device-resident throughput (`value`) ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = vlg_b200.launch_count()
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    launches = vlg_b200.launch_count() - n0
+    ms_total = e0.elapsed_time(e1)
+    t_step = torch.tensor([ms_total / args.steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
+    ms_per_step = t_step.item()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel timing (same stream, CUDA events between the launches) ----
+    reps = min(args.steps, 20)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
+    barrier()
+    for i in range(reps):
+        evs[i][0].record(stream)
+        step(i, evs[i])
+    barrier()
+    k1 = sorted(e[0].elapsed_time(e[1]) for e in evs)[reps // 2]   # count_valid + pass 1
+    k2 = sorted(e[2].elapsed_time(e[3]) for e in evs)[reps // 2]   # far path (idle) + pass 2
+    kr = sorted(e[1].elapsed_time(e[2]) for e in evs)[reps // 2]
+
+    # ---- timed region 2: end to end through the public module API from pinned host memory ----
+    host = {k: v.cpu().pin_memory() for k, v in sets[0].items()}
+    crit = vlg_b200.WarpLoss(weights=(40.0, 20.0, 10.0, 0.5))
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def e2e_step():
+        a = host["src_rgb"].to(dev, non_blocking=True).requires_grad_(with_src)
+        b = host["src_layout"].to(dev, non_blocking=True).requires_grad_(with_src)
+        f = host["flow"].to(dev, non_blocking=True).requires_grad_(True)
+        t = host["tgt_rgb"].to(dev, non_blocking=True)
+        l = host["tgt_label"].to(dev, non_blocking=True)
+        total = crit(a, b, f, t, l)
+        total.backward()
+        return crit.last_terms.cpu()       # device -> host read of the step's result (synchronises)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(n_e2e):
+        e2e_step()
+    e3.record(stream)
+    barrier()
+    t_e2e = torch.tensor([e2.elapsed_time(e3) / n_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    bpp = BYTES_PER_PX[dtype]
+    step_bytes = bpp["step"] if with_src else bpp["pass1"]
+    value = world * P / (ms_per_step * 1e-3) / 1e6
+    dom_name, dom_ms, dom_bytes = ("pass1_kernel", k1, bpp["pass1"]) if (k1 >= k2 or not with_src) else ("pass2_kernel", k2, bpp["pass2"])
+    achieved = P * dom_bytes / (dom_ms * 1e-3) / 1e9
+    out = {
+        "metric": "warp+loss fwd/bwd throughput", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {N}x{H}x{W} K={K} {dtype} warp+loss fwd+bwd per GPU"
+                               + ("" if with_src else " (flow-grad only)"),
+                   "per_gpu_pixels": P, "grads": "flow,src_rgb,src_layout" if with_src else "flow",
+                   "l2_policy": "inputs (%.0f MB/step) exceed the 126 MB L2; two input sets alternate" % (P * 120 / 1e6),
+                   "parallelism": f"dp{world}"},
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_px": dom_bytes, "kernel_ms": dom_ms},
+        "roofline_step": {"algorithmic_bytes_per_px": step_bytes,
+                          "achieved": P * step_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "frac": P * step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                          "kernel_ms": {"count+pass1": k1, "reduce": kr, "far+pass2": k2}},
+        "e2e": {"value": world * P / (t_e2e.item() * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": _cabi.LOSS_SLOTS * 4, "ms_per_step": t_e2e.item()},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n_sample = min(N, 4)
+        v, t = cpu_oracle_throughput(N, H, W, K, sigma, far, n_sample, iters=5)
+        out["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{n_sample}x{H}x{W} slice of the batch, torch CPU oracle port fwd+bwd, median of 5 ({t*1e3:.0f} ms/iter)"}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+/* vlg_b200.h -- C ABI of the B200-native flow-guided warp + per-pixel loss path.
+ *
+ * One shared library (libvlg_b200.so), built for sm_100a only, no torch types in any signature.
+ * Every entry point is stateless, re-entrant, stream-ordered and never synchronises the host;
+ * the caller owns all buffers (device pointers unless stated) and the workspace.
+ *
+ * The reference (gongaa/video-layout-generation) has NO plugin / operator / FFI layer for this
+ * path: its boundary is a set of Python call signatures.  Each entry point
+ * below names the reference interface it stands behind:
+ *
+ *   vlg_pixel_loss_*      <- criterionL1(img, frame3)                 src/trainer.py:130,248,329
+ *                            loss(output=img, target=frame3)          src/loss.py:20-25 (GradientLoss),
+ *                                                                     src/loss.py:64-91 (SsimLoss), :61-62
+ *                            cross_entropy_loss(input=seg, target=seg3)  src/trainer.py:124,250,331
+ *                            composition 40/20/10                     src/trainer.py:248-251
+ *   vlg_warp_fwd          <- (absent upstream) F.grid_sample(bilinear, align_corners=True) on the
+ *                            src/models/modules.py:69 grid + torch.argmax(seg, 1) src/trainer.py:342,467
+ *   vlg_warp_loss_*       <- the fused op that replaces src/trainer.py:248-258 when the producer
+ *                            emits flow instead of pixels
+ *   vlg_reduce_partials   <- the scalar losses handed to Trainer.sync  src/trainer.py:381-386
+ *
+ * Memory layout: activations are NHWC ("channels_last" storage of an NCHW-logical tensor),
+ * dense, 16-byte aligned base pointers.  coords / d_coords are [N,H,W,2] fp32 (x/u first),
+ * labels and argmax are int64 [N,H,W] (src/folder.py:100).
+ */
+#ifndef VLG_B200_H
+#define VLG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLG_VERSION 100 /* major*100 + minor */
+
+/* activation dtype (coords, d_coords, loss outputs are always fp32; labels int64) */
+#define VLG_F32 0
+#define VLG_BF16 1
+
+/* padding_mode of the sampler (oracle default = border) */
+#define VLG_PAD_ZEROS 0
+#define VLG_PAD_BORDER 1
+
+/* what `coords` holds */
+#define VLG_COORD_FLOW 0 /* pixel-unit flow; grid = base + flow*2/(S-1) is built in-kernel */
+#define VLG_COORD_GRID 1 /* a ready normalised sampling grid (align_corners=True)          */
+
+/* flags */
+#define VLG_FLAG_NO_FAR_PATH 1u /* caller asserts |displacement| < VLG_NEAR_RADIUS; far taps raise status */
+
+/* term_mask bits */
+#define VLG_TERM_L1 1u
+#define VLG_TERM_GD 2u
+#define VLG_TERM_SSIM 4u
+#define VLG_TERM_CE 8u
+#define VLG_TERM_TV 16u
+#define VLG_TERM_ALL 31u
+
+/* error codes (negative) */
+#define VLG_OK 0
+#define VLG_ERR_ARG (-1)
+#define VLG_ERR_UNSUPPORTED (-2)
+#define VLG_ERR_CUDA (-3)
+#define VLG_ERR_WORKSPACE (-4)
+
+/* bits of the device status word (see vlg_read_status) */
+#define VLG_STATUS_BAD_LABEL 1u  /* label outside [0,K) and != ignore_index */
+#define VLG_STATUS_FAR_TAPS 2u   /* displacement >= VLG_NEAR_RADIUS while VLG_FLAG_NO_FAR_PATH was set */
+
+/* Displacements below this many pixels take the atomics-free gather; larger ones the
+ * fixed-point (integer, hence order-independent) far path. */
+#define VLG_NEAR_RADIUS 3
+
+/* slots of the fp32 loss vector written by vlg_reduce_partials */
+#define VLG_LOSS_L1 0
+#define VLG_LOSS_GD 1
+#define VLG_LOSS_SSIM 2
+#define VLG_LOSS_CE 3
+#define VLG_LOSS_TV 4
+#define VLG_LOSS_TOTAL 5   /* w_l1*L1 + w_gd*GD + w_ssim*SSIM + w_ce*CE + w_tv*TV (src/trainer.py:248-251) */
+#define VLG_LOSS_NVALID 6  /* number of labels != ignore_index                                       */
+#define VLG_LOSS_MAXDISP 7 /* max |sampling displacement| in pixels seen by the pass                */
+#define VLG_LOSS_SLOTS 8
+
+typedef struct vlg_problem {
+    int64_t N, H, W, K;   /* batch, output height/width (== source size), layout classes          */
+    int32_t dtype;        /* VLG_F32 | VLG_BF16                                                    */
+    int32_t padding;      /* VLG_PAD_*                                                             */
+    int32_t coord_mode;   /* VLG_COORD_*                                                           */
+    uint32_t flags;       /* VLG_FLAG_*                                                            */
+    int64_t ignore_index; /* nn.CrossEntropyLoss default -100 (src/trainer.py:124)                 */
+    float w_l1, w_gd, w_ssim, w_ce, w_tv; /* 40, 20, 20, 10 (src/trainer.py:248-250) + TV weight  */
+    uint32_t term_mask;   /* VLG_TERM_* bits to evaluate; 0 = all.  Skipped terms read as 0.       */
+    uint32_t reserved;
+    /* Divisors of the means.  0 = derive from N,H,W (single GPU).  Data-parallel ranks pass the
+     * GLOBAL batch here so that per-rank loss vectors and gradients simply add. */
+    int64_t global_N;
+} vlg_problem_t;
+
+int vlg_version(void);
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char *vlg_last_error(void);
+
+/* Bytes of caller-supplied device workspace needed by the vlg_warp_loss_* / vlg_pixel_loss_*
+ * entry points for this problem (16-byte aligned; contents need no initialisation).
+ * `with_src_grad` != 0 adds the d_out staging the deterministic source-gradient pass reads. */
+size_t vlg_workspace_bytes(const vlg_problem_t *prob, int with_src_grad);
+
+/* Forward warp only (validation / rollout, src/trainer.py:329-342,460-469):
+ *   out_rgb    [N,H,W,3]  = warp(src_rgb)         (nullable)
+ *   out_layout [N,H,W,K]  = warp(src_layout)      (nullable)
+ *   out_argmax [N,H,W] i64 = argmax_k out_layout  (nullable; first max on ties)
+ *   dbg_x0y0   [N,H,W,2] i32 floor source indices (nullable; bit-exact index witness) */
+int vlg_warp_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout,
+                 const float *coords, void *out_rgb, void *out_layout, int64_t *out_argmax,
+                 int32_t *dbg_x0y0, void *stream);
+
+/* Pass 1 of the fused op: warp + all loss terms + d(loss)/d(warped) + d(loss)/d(coords) in one
+ * kernel.  Gradients are for an upstream grad of 1.0 (see vlg_scale_grads).
+ *   tgt_rgb [N,H,W,3], tgt_label [N,H,W] i64
+ *   d_coords [N,H,W,2] fp32 (nullable = forward/validation only: no gradient work, no d_out)
+ *   out_argmax nullable.
+ * Writes per-block partial sums and (if with_src_grad) d_out into `workspace`. */
+int vlg_warp_loss_bwd_out(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout,
+                          const float *coords, const void *tgt_rgb, const int64_t *tgt_label,
+                          float *d_coords, int64_t *out_argmax, int with_src_grad,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* Pass 2: deterministic source gradient (no float atomics): every source pixel gathers, in a
+ * fixed order, the d_out of the output pixels whose bilinear footprint covers it.
+ *   d_src_rgb [N,H,W,3], d_src_layout [N,H,W,K] (either nullable) */
+int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src_rgb,
+                     void *d_src_layout, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Fixed-order fp64 reduction of the per-block partials into loss_out[VLG_LOSS_SLOTS] (fp32). */
+int vlg_reduce_partials(const vlg_problem_t *prob, float *loss_out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* Convenience: pass 1 + reduce (+ pass 2 when d_src_* given) on one stream. */
+int vlg_warp_loss_fwd_bwd(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout,
+                          const float *coords, const void *tgt_rgb, const int64_t *tgt_label,
+                          float *loss_out, float *d_coords, void *d_src_rgb, void *d_src_layout,
+                          int64_t *out_argmax, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The reference's own loss call sites without a warp: `output` rgb [N,H,W,3] vs `target`,
+ * `logits` [N,H,W,K] vs `tgt_label`.  Any of (out_rgb+tgt_rgb) / (logits+tgt_label) may be NULL
+ * to evaluate a single criterion.  d_out_rgb / d_logits nullable (validation).  prob->coord_mode
+ * and padding are ignored. */
+int vlg_pixel_loss_fwd_bwd(const vlg_problem_t *prob, const void *out_rgb, const void *tgt_rgb,
+                           const void *logits, const int64_t *tgt_label, float *loss_out,
+                           void *d_out_rgb, void *d_logits, int64_t *out_argmax, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
+/* g <- g * (*scale) for n fp32/bf16 elements; exits at once when *scale == 1.0f (the common
+ * `loss.backward()` case), so autograd semantics cost one empty launch.  `scale` is a device ptr. */
+int vlg_scale_grads(void *g, int64_t n, int32_t dtype, const float *scale, void *stream);
+
+/* Copies the device status word (VLG_STATUS_*) to *host_status.  Synchronises `stream`. */
+int vlg_read_status(void *workspace, size_t workspace_bytes, uint32_t *host_status, void *stream);
+
+/* Number of kernels the library has launched in this process (for bench.py's gpu_launches). */
+int64_t vlg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLG_B200_H */

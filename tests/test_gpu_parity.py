@@ -1,0 +1,324 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+ (1) the committed golden fixtures (real reference loss modules + torch 2.11 CPU grid_sample),
+ (2) the oracle (oracle/torch_oracle.py, oracle/warp_oracle.c) on seeded inputs,
+ (3) size-independent properties at BASELINE.json's full sizes.
+
+Bars (BASELINE.json north_star): sampling indices and argmax bit-exact; losses and gradients
+within 1e-5 relative in fp32.  For gradient tensors "relative" is normwise:
+max|g - g_ref| <= 1e-5 * max|g_ref| (element-wise relative error is meaningless where terms cancel).
+"""
+import numpy as np
+import pytest
+import torch
+
+import vlg_b200
+from vlg_b200 import _cabi
+from conftest import golden_names, load_golden
+from oracle import c_oracle as CO
+from oracle import torch_oracle as TO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL = 1e-5
+TERMS = ["l1", "gd", "ssim", "ce", "tv"]
+
+
+def _cl(x):  # NCHW numpy/tensor -> channels_last CUDA tensor
+    t = torch.as_tensor(x).to(DEV)
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+def _nchw(t):
+    return t.detach().float().cpu().contiguous().numpy()
+
+
+def _assert_close_norm(got, ref, rtol, what):
+    err = np.abs(got - ref).max()
+    scale = np.abs(ref).max()
+    assert err <= rtol * scale + 1e-30, f"{what}: max err {err:.3e} vs {rtol:g} * {scale:.3e}"
+
+
+def _cfg(g, **kw):
+    return vlg_b200.WarpLossConfig(w_tv=g["w_tv"], padding_mode=g["padding"], **kw)
+
+
+# ------------------------------------------------------------------ goldens: forward warp
+@pytest.mark.parametrize("name", golden_names())
+def test_warp_forward_bit_exact_vs_golden(name):
+    g = load_golden(name)
+    flow = torch.as_tensor(g["flow"]).to(DEV)
+    out_rgb, out_lay, arg, dbg = vlg_b200.warp(_cl(g["src_rgb"]), _cl(g["src_layout"]), flow,
+                                               padding_mode=g["padding"], debug_indices=True)
+    assert (_bits(_nchw(out_rgb)) == _bits(g["warped_rgb"])).all()
+    assert (_bits(_nchw(out_lay)) == _bits(g["warped_layout"])).all()
+    assert (arg.cpu().numpy() == g["argmax"]).all()
+    # sampling indices against the strict-fp32 C restatement
+    _, x0y0, _ = CO.sample_coords(g["grid"], g["padding"])
+    inr = (np.abs(x0y0) < 2 ** 20).all(-1)
+    assert (dbg.cpu().numpy()[inr] == x0y0[inr]).all()
+    # grid mode consumes the same fp32 grid tensor and must agree bit for bit as well
+    o2, l2, a2 = vlg_b200.warp(_cl(g["src_rgb"]), _cl(g["src_layout"]), torch.as_tensor(g["grid"]).to(DEV),
+                               padding_mode=g["padding"], coords_are_grid=True)
+    assert torch.equal(o2, out_rgb) and torch.equal(l2, out_lay) and torch.equal(a2, arg)
+
+
+# ------------------------------------------------------------------ goldens: fused loss + grads
+@pytest.mark.parametrize("name", golden_names())
+def test_warp_loss_fwd_bwd_vs_golden(name):
+    g = load_golden(name)
+    a = _cl(g["src_rgb"]).requires_grad_(True)
+    b = _cl(g["src_layout"]).requires_grad_(True)
+    f = torch.as_tensor(g["flow"]).to(DEV).requires_grad_(True)
+    total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(g["tgt_rgb"]), torch.as_tensor(g["tgt_label"]).to(DEV),
+                                         _cfg(g, want_argmax=True))
+    total.backward()
+    vec = vec.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(vec[:5], g["terms"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(vec[_cabi.LOSS_TOTAL], g["total"], rtol=RTOL)
+    assert (arg.cpu().numpy() == g["argmax"]).all()
+    _assert_close_norm(_nchw(f.grad), g["d_flow"], RTOL, "d_flow")
+    _assert_close_norm(_nchw(a.grad), g["d_src_rgb"], RTOL, "d_src_rgb")
+    _assert_close_norm(_nchw(b.grad), g["d_src_layout"], RTOL, "d_src_layout")
+
+
+def test_flow_grad_only_matches_full(golden):
+    g = golden
+    f = torch.as_tensor(g["flow"]).to(DEV).requires_grad_(True)
+    total, vec, _ = vlg_b200.warp_loss(_cl(g["src_rgb"]), _cl(g["src_layout"]), f, _cl(g["tgt_rgb"]),
+                                       torch.as_tensor(g["tgt_label"]).to(DEV), _cfg(g))
+    total.backward()
+    _assert_close_norm(_nchw(f.grad), g["d_flow"], RTOL, "d_flow")
+    # validation mode: no gradient requested at all
+    with torch.no_grad():
+        t2, v2, _ = vlg_b200.warp_loss(_cl(g["src_rgb"]), _cl(g["src_layout"]), f.detach(), _cl(g["tgt_rgb"]),
+                                       torch.as_tensor(g["tgt_label"]).to(DEV), _cfg(g))
+    assert torch.equal(v2[:6], vec[:6])
+
+
+# ------------------------------------------------------------------ reference call sites (no warp)
+@pytest.mark.parametrize("name", golden_names())
+def test_reference_criteria_modules(name):
+    g = load_golden(name)
+    img = _cl(g["warped_rgb"]).requires_grad_(True)
+    seg = _cl(g["warped_layout"]).requires_grad_(True)
+    frame3 = _cl(g["tgt_rgb"])
+    seg3 = torch.as_tensor(g["tgt_label"]).to(DEV)
+    # same three lines as src/trainer.py:248-250
+    loss_G_L1 = vlg_b200.L1Loss()(img, frame3) * 40
+    style_loss = vlg_b200.CombinedLoss()(output=img, target=frame3) * 20
+    seg_loss = vlg_b200.CrossEntropyLoss()(input=seg, target=seg3) * 10
+    loss_G = loss_G_L1 + style_loss + seg_loss
+    loss_G.backward()
+    t = g["terms"]
+    np.testing.assert_allclose(loss_G_L1.item(), 40 * t[0], rtol=RTOL)
+    np.testing.assert_allclose(style_loss.item(), 20 * (t[1] + t[2]), rtol=RTOL)
+    np.testing.assert_allclose(seg_loss.item(), 10 * t[3], rtol=RTOL)
+    # gradients against torch autograd on the oracle composition
+    a = torch.as_tensor(g["warped_rgb"]).clone().requires_grad_(True)
+    z = torch.as_tensor(g["warped_layout"]).clone().requires_grad_(True)
+    ref = (40 * TO.l1_loss(a, torch.as_tensor(g["tgt_rgb"]))
+           + 20 * (TO.gradient_loss(a, torch.as_tensor(g["tgt_rgb"])) + TO.ssim_loss(a, torch.as_tensor(g["tgt_rgb"])))
+           + 10 * TO.cross_entropy(z, torch.as_tensor(g["tgt_label"])))
+    ref.backward()
+    _assert_close_norm(_nchw(img.grad), a.grad.numpy(), RTOL, "d_img")
+    _assert_close_norm(_nchw(seg.grad), z.grad.numpy(), RTOL, "d_seg")
+    # the fused single-launch composition agrees with the three separate criteria
+    img2 = _cl(g["warped_rgb"]).requires_grad_(True)
+    seg2 = _cl(g["warped_layout"]).requires_grad_(True)
+    fused = vlg_b200.PixelLosses()(img2, frame3, seg2, seg3)
+    fused.backward()
+    np.testing.assert_allclose(fused.item(), loss_G.item(), rtol=RTOL)
+    _assert_close_norm(_nchw(img2.grad), _nchw(img.grad), RTOL, "fused d_img")
+    _assert_close_norm(_nchw(seg2.grad), _nchw(seg.grad), RTOL, "fused d_seg")
+    # single criteria
+    for mod, fn in ((vlg_b200.GradientLoss(), TO.gradient_loss), (vlg_b200.SsimLoss(), TO.ssim_loss)):
+        got = mod(_cl(g["warped_rgb"]), frame3).item()
+        np.testing.assert_allclose(got, fn(torch.as_tensor(g["warped_rgb"]), torch.as_tensor(g["tgt_rgb"])).item(), rtol=RTOL)
+
+
+def test_nchw_contiguous_inputs_are_accepted(golden):
+    """Plain NCHW-contiguous tensors (the reference's layout) get one permute-copy and the same result."""
+    g = golden
+    f = torch.as_tensor(g["flow"]).to(DEV)
+    lab = torch.as_tensor(g["tgt_label"]).to(DEV)
+    t1, v1, _ = vlg_b200.warp_loss(_cl(g["src_rgb"]), _cl(g["src_layout"]), f, _cl(g["tgt_rgb"]), lab, _cfg(g))
+    nchw = lambda k: torch.as_tensor(g[k]).to(DEV).contiguous()
+    t2, v2, _ = vlg_b200.warp_loss(nchw("src_rgb"), nchw("src_layout"), f, nchw("tgt_rgb"), lab, _cfg(g))
+    assert torch.equal(v1, v2)
+
+
+# ------------------------------------------------------------------ seeded cases vs the oracle
+def _make_case(N, H, W, K, sigma, seed, layout="onehot", far_frac=0.0, device=DEV):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    mean = torch.tensor([0.485, 0.456, 0.406])[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225])[None, :, None, None]
+    src_rgb = (torch.rand(N, 3, H, W, generator=g) - mean) / std
+    tgt_rgb = (torch.rand(N, 3, H, W, generator=g) - mean) / std
+    blk = 32
+    def labels():
+        l = torch.randint(0, K, (N, (H + blk - 1) // blk, (W + blk - 1) // blk), generator=g)
+        return l.repeat_interleave(blk, 1).repeat_interleave(blk, 2)[:, :H, :W].contiguous()
+    lab_src, lab_tgt = labels(), labels()
+    src_layout = TO.one_hot_layout(lab_src, K).contiguous() if layout == "onehot" else torch.randn(N, K, H, W, generator=g)
+    flow = torch.randn(N, 2, H, W, generator=g) * sigma
+    flow = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(flow, (4, 4, 4, 4), mode="replicate"), 9, 1)
+    if far_frac > 0:
+        m = torch.rand(N, 1, H, W, generator=g) < far_frac
+        far = (torch.rand(N, 2, H, W, generator=g) - 0.5) * 2 * max(H, W)
+        flow = torch.where(m, far, flow)
+    flow = flow.permute(0, 2, 3, 1).contiguous()
+    return dict(src_rgb=src_rgb, src_layout=src_layout, flow=flow, tgt_rgb=tgt_rgb, tgt_label=lab_tgt)
+
+
+CASES = [
+    # N, H, W, K, sigma, layout, far_frac, w_tv, padding
+    (2, 128, 256, 20, 4.0, "onehot", 0.0, 0.5, "border"),      # BASELINE config 1
+    (1, 375, 1242, 20, 48.0, "soft", 0.05, 0.1, "border"),     # KITTI-shaped, large displacement + outliers
+    (2, 67, 129, 20, 12.0, "soft", 0.0, 1.0, "zeros"),         # ragged tiles, zeros padding
+    (1, 33, 35, 5, 2.0, "soft", 0.0, 0.0, "border"),           # small K
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}x{c[1]}x{c[2]}k{c[3]}s{c[4]}{c[8]}" for c in CASES])
+def test_seeded_case_vs_oracle(case):
+    N, H, W, K, sigma, layout, far, w_tv, padding = case
+    d = _make_case(N, H, W, K, sigma, seed=1024, layout=layout, far_frac=far)
+    ref = TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"],
+                               w_tv=w_tv, padding_mode=padding)
+    a = _cl(d["src_rgb"]).requires_grad_(True)
+    b = _cl(d["src_layout"]).requires_grad_(True)
+    f = d["flow"].to(DEV).requires_grad_(True)
+    cfg = vlg_b200.WarpLossConfig(w_tv=w_tv, padding_mode=padding, want_argmax=True)
+    total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV), cfg)
+    total.backward()
+    # forward pieces bit-exact through the forward-only entry point
+    o_rgb, o_lay, o_arg = vlg_b200.warp(a.detach(), b.detach(), f.detach(), padding_mode=padding)
+    assert (_bits(_nchw(o_rgb)) == _bits(ref["warped_rgb"].detach().numpy())).all()
+    assert (_bits(_nchw(o_lay)) == _bits(ref["warped_layout"].detach().numpy())).all()
+    assert torch.equal(o_arg.cpu(), ref["argmax"]) and torch.equal(arg.cpu(), ref["argmax"])
+    got = vec.cpu().numpy().astype(np.float64)
+    want = np.array([ref["terms"][k].item() for k in TERMS])
+    np.testing.assert_allclose(got[:5], want, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(got[_cabi.LOSS_TOTAL], ref["total"].item(), rtol=RTOL)
+    _assert_close_norm(_nchw(f.grad), ref["d_flow"].numpy(), RTOL, "d_flow")
+    _assert_close_norm(_nchw(a.grad), ref["d_src_rgb"].numpy(), RTOL, "d_src_rgb")
+    _assert_close_norm(_nchw(b.grad), ref["d_src_layout"].numpy(), RTOL, "d_src_layout")
+    # C restatement as second witness of the loss terms
+    np.testing.assert_allclose(got[0], CO.l1(_nchw(o_rgb), d["tgt_rgb"].numpy()), rtol=RTOL)
+    np.testing.assert_allclose(got[2], CO.ssim(_nchw(o_rgb), d["tgt_rgb"].numpy()), rtol=RTOL)
+
+
+def test_gradients_are_deterministic_and_far_path_runs():
+    """Bitwise-identical gradients over repeated runs, with and without far (fixed-point) pixels."""
+    for far in (0.0, 0.05):
+        d = _make_case(2, 96, 160, 20, 6.0, seed=7, layout="soft", far_frac=far)
+        outs = []
+        for _ in range(5):
+            a = _cl(d["src_rgb"]).requires_grad_(True)
+            b = _cl(d["src_layout"]).requires_grad_(True)
+            f = d["flow"].to(DEV).requires_grad_(True)
+            total, vec, _ = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV),
+                                               vlg_b200.WarpLossConfig(w_tv=0.3))
+            total.backward()
+            outs.append((vec.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+        for o in outs[1:]:
+            for x, y in zip(o, outs[0]):
+                assert torch.equal(x, y)
+        md = outs[0][0][_cabi.LOSS_MAXDISP].item()
+        assert (md >= _cabi.NEAR_RADIUS) == (far > 0)
+
+
+def test_upstream_gradient_scaling():
+    d = _make_case(1, 40, 72, 20, 2.0, seed=3)
+    grads = []
+    for scale in (1.0, 0.125):
+        a = _cl(d["src_rgb"]).requires_grad_(True)
+        f = d["flow"].to(DEV).requires_grad_(True)
+        total, _, _ = vlg_b200.warp_loss(a, _cl(d["src_layout"]), f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV))
+        (total * scale).backward()
+        grads.append((a.grad.clone(), f.grad.clone()))
+    for g1, g2 in zip(*grads):
+        assert torch.equal(g1 * 0.125, g2)   # power-of-two scale is exact
+
+
+def test_ignore_index_and_bad_label_status():
+    d = _make_case(1, 32, 64, 20, 1.0, seed=5, layout="soft")
+    lab = d["tgt_label"].clone()
+    lab[0, :8] = -100
+    ref = TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], lab)
+    b = _cl(d["src_layout"]).requires_grad_(True)
+    total, vec, _ = vlg_b200.warp_loss(_cl(d["src_rgb"]), b, d["flow"].to(DEV), _cl(d["tgt_rgb"]), lab.to(DEV))
+    total.backward()
+    np.testing.assert_allclose(vec[_cabi.LOSS_CE].item(), ref["terms"]["ce"].item(), rtol=RTOL)
+    assert vec[_cabi.LOSS_NVALID].item() == (lab != -100).sum().item()
+    _assert_close_norm(_nchw(b.grad), ref["d_src_layout"].numpy(), RTOL, "d_src_layout")
+
+
+def test_assume_near_matches_default_path():
+    d = _make_case(2, 64, 96, 20, 3.0, seed=11)
+    res = []
+    for near in (False, True):
+        b = _cl(d["src_layout"]).requires_grad_(True)
+        total, vec, _ = vlg_b200.warp_loss(_cl(d["src_rgb"]), b, d["flow"].to(DEV), _cl(d["tgt_rgb"]),
+                                           d["tgt_label"].to(DEV), vlg_b200.WarpLossConfig(assume_near=near))
+        total.backward()
+        res.append((vec.clone(), b.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config 2)
+def test_full_size_properties_config2():
+    """16x256x512, K=20 (BASELINE.json configs[1]): compare against the oracle evaluated by torch on
+    the same GPU, plus size-independent properties."""
+    N, H, W, K = 16, 256, 512, 20
+    d = _make_case(N, H, W, K, 4.0, seed=1024)
+    a = _cl(d["src_rgb"]).requires_grad_(True)
+    b = _cl(d["src_layout"]).requires_grad_(True)
+    f = d["flow"].to(DEV).requires_grad_(True)
+    tgt, lab = _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV)
+    total, vec, arg = vlg_b200.warp_loss(a, b, f, tgt, lab, vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
+    total.backward()
+    # oracle on the GPU (torch CUDA ops), fp32
+    ra = d["src_rgb"].to(DEV).requires_grad_(True)
+    rb = d["src_layout"].to(DEV).requires_grad_(True)
+    rf = d["flow"].to(DEV).requires_grad_(True)
+    ref = TO.warp_loss(ra, rb, rf, d["tgt_rgb"].to(DEV), lab, w_tv=0.5)
+    ref["total"].backward()
+    got = vec.cpu().numpy().astype(np.float64)
+    want = np.array([ref["terms"][k].item() for k in TERMS])
+    np.testing.assert_allclose(got[:5], want, rtol=RTOL)
+    o_rgb, o_lay, o_arg = vlg_b200.warp(a.detach(), b.detach(), f.detach())
+    assert torch.equal(o_arg, ref["argmax"]) and torch.equal(arg, ref["argmax"])
+    assert torch.equal(o_lay.contiguous(), ref["warped_layout"].detach().contiguous())   # bit-exact vs torch CUDA
+    assert torch.equal(o_rgb.contiguous(), ref["warped_rgb"].detach().contiguous())
+    _assert_close_norm(_nchw(f.grad), _nchw(rf.grad), RTOL, "d_flow")
+    _assert_close_norm(_nchw(a.grad), _nchw(ra.grad), 2e-5, "d_src_rgb")      # torch's own scatter is atomic-ordered
+    _assert_close_norm(_nchw(b.grad), _nchw(rb.grad), 2e-5, "d_src_layout")
+    # properties: one-hot sources warp to a partition of unity; gradient mass is conserved by the
+    # transpose (sum of d_src == sum of weights * d_out == d/d(eps) of loss under src += eps)
+    s = o_lay.float().sum(1)
+    assert (s - 1).abs().max().item() < 1e-5
+    assert arg.min().item() >= 0 and arg.max().item() < K
+
+
+def test_linearity_of_source_gradient_transpose():
+    """<warp(src), g> == <src, warp^T(g)> : the deterministic pass 2 is the exact adjoint of the
+    forward gather (checked through CE-free L1-only losses with random targets)."""
+    d = _make_case(1, 48, 80, 20, 5.0, seed=21, layout="soft")
+    f = d["flow"].to(DEV)
+    b = _cl(d["src_layout"]).requires_grad_(True)
+    a = _cl(d["src_rgb"]).requires_grad_(True)
+    cfg = vlg_b200.WarpLossConfig(w_l1=1.0, w_gd=0.0, w_ssim=0.0, w_ce=0.0, term_mask=_cabi.TERM_L1 | _cabi.TERM_CE)
+    total, vec, _ = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV), cfg)
+    total.backward()
+    # L1 gradient wrt warped = sign(a-b)/numel ; so <d_src, src> must equal <sign/numel, warp(src)>
+    o_rgb, _, _ = vlg_b200.warp(a.detach(), None, f)
+    gout = torch.sign(o_rgb.float() - _cl(d["tgt_rgb"])) / o_rgb.numel()
+    lhs = (a.grad.double() * a.detach().double()).sum().item()
+    rhs = (gout.double() * o_rgb.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * abs(rhs)
+    assert b.grad.abs().max().item() == 0.0   # w_ce = 0 -> no layout gradient

@@ -1,0 +1,13 @@
+"""video-layout-generation_b200: B200-native flow-guided warp + per-pixel losses (fwd/bwd).
+
+Hand-written sm_100a CUDA kernels behind a C ABI (include/vlg_b200.h, libvlg_b200.so), with the
+reference's Python call signatures on top.  Import as `vlg_b200` (see vlg_b200.py at the repo
+root; the directory name carries a hyphen).
+"""
+from . import _build, _cabi  # noqa: F401
+from ._cabi import VlgError, launch_count  # noqa: F401
+from .losses import (CombinedLoss, CrossEntropyLoss, GradientLoss, L1Loss, PixelLosses,  # noqa: F401
+                     SsimLoss, WarpLoss)
+from .ops import WarpLossConfig, empty_nhwc, pixel_losses, to_nhwc, warp, warp_loss  # noqa: F401
+
+__version__ = "1.0"

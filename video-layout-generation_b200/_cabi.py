@@ -1,0 +1,91 @@
+"""ctypes binding of include/vlg_b200.h.  No fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+F32, BF16 = 0, 1
+PAD_ZEROS, PAD_BORDER = 0, 1
+COORD_FLOW, COORD_GRID = 0, 1
+FLAG_NO_FAR_PATH = 1
+TERM_L1, TERM_GD, TERM_SSIM, TERM_CE, TERM_TV, TERM_ALL = 1, 2, 4, 8, 16, 31
+STATUS_BAD_LABEL, STATUS_FAR_TAPS = 1, 2
+NEAR_RADIUS = 3
+LOSS_L1, LOSS_GD, LOSS_SSIM, LOSS_CE, LOSS_TV, LOSS_TOTAL, LOSS_NVALID, LOSS_MAXDISP, LOSS_SLOTS = range(9)
+
+EXPORTS = [
+    "vlg_version", "vlg_last_error", "vlg_workspace_bytes", "vlg_warp_fwd", "vlg_warp_loss_bwd_out",
+    "vlg_warp_bwd_src", "vlg_reduce_partials", "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd",
+    "vlg_scale_grads", "vlg_read_status", "vlg_launch_count",
+]
+
+
+class Problem(C.Structure):
+    """Mirror of vlg_problem_t (include/vlg_b200.h)."""
+    _fields_ = [
+        ("N", C.c_int64), ("H", C.c_int64), ("W", C.c_int64), ("K", C.c_int64),
+        ("dtype", C.c_int32), ("padding", C.c_int32), ("coord_mode", C.c_int32), ("flags", C.c_uint32),
+        ("ignore_index", C.c_int64),
+        ("w_l1", C.c_float), ("w_gd", C.c_float), ("w_ssim", C.c_float), ("w_ce", C.c_float), ("w_tv", C.c_float),
+        ("term_mask", C.c_uint32), ("reserved", C.c_uint32),
+        ("global_N", C.c_int64),
+    ]
+
+
+class VlgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load libvlg_b200.so (building it in-tree first if nvcc is available and it is stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build_library()
+        except Exception as exc:  # stale-but-present library is still usable; missing is fatal
+            if not os.path.exists(path):
+                raise VlgError(f"libvlg_b200.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(path):
+        raise VlgError("libvlg_b200.so is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    vp, i64p, f32p = C.c_void_p, C.c_void_p, C.c_void_p
+    P = C.POINTER(Problem)
+    lib.vlg_version.restype = C.c_int
+    lib.vlg_last_error.restype = C.c_char_p
+    lib.vlg_launch_count.restype = C.c_int64
+    lib.vlg_workspace_bytes.restype = C.c_size_t
+    lib.vlg_workspace_bytes.argtypes = [P, C.c_int]
+    lib.vlg_warp_fwd.argtypes = [P, vp, vp, f32p, vp, vp, i64p, vp, vp]
+    lib.vlg_warp_loss_bwd_out.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, i64p, C.c_int, vp, C.c_size_t, vp]
+    lib.vlg_warp_bwd_src.argtypes = [P, f32p, vp, vp, vp, C.c_size_t, vp]
+    lib.vlg_reduce_partials.argtypes = [P, f32p, vp, C.c_size_t, vp]
+    lib.vlg_warp_loss_fwd_bwd.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, f32p, vp, vp, i64p, vp, C.c_size_t, vp]
+    lib.vlg_pixel_loss_fwd_bwd.argtypes = [P, vp, vp, vp, i64p, f32p, vp, vp, i64p, vp, C.c_size_t, vp]
+    lib.vlg_scale_grads.argtypes = [vp, C.c_int64, C.c_int32, f32p, vp]
+    lib.vlg_read_status.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint32), vp]
+    for name in ("vlg_warp_fwd", "vlg_warp_loss_bwd_out", "vlg_warp_bwd_src", "vlg_reduce_partials",
+                 "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd", "vlg_scale_grads", "vlg_read_status"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise VlgError(f"vlg error {rc}: {load().vlg_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().vlg_launch_count())

@@ -1,0 +1,436 @@
+// vlg_api.cu -- the C ABI declared in include/vlg_b200.h: argument checks, workspace carving,
+// kernel launches.  No allocation, no host synchronisation (except vlg_read_status), no torch.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "vlg_pass1.cuh"
+#include "vlg_pass2.cuh"
+
+using namespace vlg;
+
+// Layout class counts compiled in (Cityscapes trainer: 20, src/models/gridnet.py:9; the others
+// cover the reference's alternative heads and the small-K parity fixtures).
+#define VLG_FOR_EACH_K(X) X(20) X(5)
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int check_launch(const char *what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return VLG_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static bool k_supported(int64_t K) {
+#define X(k) if (K == k) return true;
+    VLG_FOR_EACH_K(X)
+#undef X
+    return false;
+}
+
+static int check_problem(const vlg_problem_t *p) {
+    if (!p) return fail(VLG_ERR_ARG, "problem is NULL");
+    if (p->N < 1 || p->H < 2 || p->W < 2) return fail(VLG_ERR_ARG, "need N>=1, H>=2, W>=2 (got %lld,%lld,%lld)", (long long)p->N, (long long)p->H, (long long)p->W);
+    if (p->N * p->H * p->W >= (1ll << 31)) return fail(VLG_ERR_UNSUPPORTED, "N*H*W must be < 2^31");
+    if (!k_supported(p->K)) return fail(VLG_ERR_UNSUPPORTED, "K=%lld not compiled in (see VLG_FOR_EACH_K)", (long long)p->K);
+    if (p->dtype != VLG_F32 && p->dtype != VLG_BF16) return fail(VLG_ERR_ARG, "bad dtype %d", p->dtype);
+    if (p->padding != VLG_PAD_ZEROS && p->padding != VLG_PAD_BORDER) return fail(VLG_ERR_ARG, "bad padding %d", p->padding);
+    if (p->coord_mode != VLG_COORD_FLOW && p->coord_mode != VLG_COORD_GRID) return fail(VLG_ERR_ARG, "bad coord_mode %d", p->coord_mode);
+    if (p->global_N != 0 && p->global_N < p->N) return fail(VLG_ERR_ARG, "global_N < N");
+    return VLG_OK;
+}
+
+static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
+    WsLayout L{};
+    const size_t P = (size_t)p->N * p->H * p->W;
+    L.n_blocks = p->N * tiles_x(p->W) * tiles_y(p->H);
+    size_t off = 0;
+    L.header = off; off = align_up(off + sizeof(WsHeader), 256);
+    L.partials = off; off = align_up(off + (size_t)L.n_blocks * kPartialSlots * sizeof(float), 256);
+    L.dout_rgb = L.dout_lay = L.far_acc = 0;
+    if (with_src_grad) {
+        L.dout_rgb = off; off = align_up(off + P * 3 * sizeof(float), 256);
+        L.dout_lay = off; off = align_up(off + P * p->K * sizeof(float), 256);
+        if (!(p->flags & VLG_FLAG_NO_FAR_PATH)) {
+            L.far_acc = off; off = align_up(off + P * (3 + p->K) * sizeof(long long), 256);
+        }
+    }
+    L.total = off;
+    return L;
+}
+
+static CoordCfg make_cc(const vlg_problem_t *p) {
+    CoordCfg cc;
+    cc.H = (int)p->H; cc.W = (int)p->W;
+    cc.padding = p->padding; cc.coord_mode = p->coord_mode;
+    cc.Wm1 = (float)(p->W - 1); cc.Hm1 = (float)(p->H - 1);
+    cc.sx = (float)(2.0 / (double)(p->W - 1));
+    cc.sy = (float)(2.0 / (double)(p->H - 1));
+    return cc;
+}
+
+// ------------------------------------------------------------------ small kernels
+__global__ void count_valid_kernel(const int64_t *__restrict__ label, int64_t P, int64_t ignore_index, WsHeader *hdr) {
+    unsigned int cnt = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride)
+        cnt += __ldg(label + i) != ignore_index;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    __shared__ unsigned int s[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s[wid] = cnt;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int v = lane < (blockDim.x >> 5) ? s[lane] : 0u;
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (lane == 0 && v) atomicAdd(&hdr->n_valid, (unsigned long long)v);
+    }
+}
+
+struct ReduceParams {
+    const float *partials;
+    int64_t n_blocks;
+    const WsHeader *hdr;
+    double inv_numel_rgb;   // 1/(Ng*3*H*W)
+    double inv_ssim;        // 1/(Ng*(H-2)*(W-2))
+    double inv_tvh, inv_tvw;
+    double ce_scale;        // N_local/N_global
+    float w_l1, w_gd, w_ssim, w_ce, w_tv;
+    float *out;
+};
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
+    __shared__ double s[6][256];
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t b = threadIdx.x; b < p.n_blocks; b += 256) {
+        const float4 lo = __ldg(reinterpret_cast<const float4 *>(p.partials + b * kPartialSlots));
+        const float2 hi = __ldg(reinterpret_cast<const float2 *>(p.partials + b * kPartialSlots + 4));
+        acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w; acc[4] += hi.x; acc[5] += hi.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i][threadIdx.x] = acc[i];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s[i][threadIdx.x] += s[i][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double nv = (double)p.hdr->n_valid;
+        const double l1 = s[0][0] * p.inv_numel_rgb, gd = s[1][0] * p.inv_numel_rgb;
+        const double ssim = s[2][0] * p.inv_ssim;
+        const double ce = nv > 0 ? s[3][0] / nv * p.ce_scale : 0.0;
+        const double tv = s[4][0] * p.inv_tvh + s[5][0] * p.inv_tvw;
+        p.out[VLG_LOSS_L1] = (float)l1;
+        p.out[VLG_LOSS_GD] = (float)gd;
+        p.out[VLG_LOSS_SSIM] = (float)ssim;
+        p.out[VLG_LOSS_CE] = (float)ce;
+        p.out[VLG_LOSS_TV] = (float)tv;
+        const double tot = (double)p.w_l1 * l1 + (double)p.w_gd * gd + (double)p.w_ssim * ssim +
+                           (double)p.w_ce * ce + (double)p.w_tv * tv;
+        p.out[VLG_LOSS_TOTAL] = (float)tot;
+        p.out[VLG_LOSS_NVALID] = (float)nv;
+        p.out[VLG_LOSS_MAXDISP] = __uint_as_float(p.hdr->maxdisp_bits);
+    }
+}
+
+template <typename T>
+__global__ void scale_kernel(T *g, int64_t n, const float *scale) {
+    const float s = __ldg(scale);
+    if (s == 1.0f) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        g[i] = from_f<T>(to_f<T>(g[i]) * s);
+}
+
+// forward-only warp (validation / rollout): one thread per output pixel
+template <typename T, int K>
+__global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, int64_t HW, const T *__restrict__ src_rgb,
+                                                       const T *__restrict__ src_lay, const float2 *__restrict__ coords,
+                                                       T *out_rgb, T *out_lay, int64_t *out_argmax, int2 *dbg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int64_t n = i / HW, rem = i - n * HW;
+    const int y = (int)(rem / cc.W), x = (int)(rem - (int64_t)y * cc.W);
+    const Taps t = make_taps(cc, __ldg(coords + i), y, x);
+    if (dbg) dbg[i] = make_int2((int)t.fx0, (int)t.fy0);
+    if (src_rgb && out_rgb) {
+        float a[3];
+        gather_px<T, 3>(src_rgb + n * HW * 3, cc, t, a);
+        store_px<T, 3>(out_rgb + i * 3, a);
+    }
+    if (src_lay && (out_lay || out_argmax)) {
+        float z[K];
+        gather_px<T, K>(src_lay + n * HW * K, cc, t, z);
+        if (out_lay) store_px<T, K>(out_lay + i * K, z);
+        if (out_argmax) {
+            // argmax is taken on the values as STORED (rounded to T), like torch.argmax on the output
+            float m = to_f<T>(from_f<T>(z[0]));
+            int best = 0;
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+                const float v = to_f<T>(from_f<T>(z[k]));
+                if (v > m) { m = v; best = k; }
+            }
+            out_argmax[i] = best;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ dispatch helpers
+template <typename T, int K>
+static int launch_pass1(bool warp, const Pass1Params &pp, int64_t n_blocks, cudaStream_t st) {
+    if (warp) pass1_kernel<T, K, true><<<(unsigned)n_blocks, kThreads, 0, st>>>(pp);
+    else pass1_kernel<T, K, false><<<(unsigned)n_blocks, kThreads, 0, st>>>(pp);
+    return check_launch("pass1_kernel");
+}
+
+static int dispatch_pass1(const vlg_problem_t *prob, bool warp, const Pass1Params &pp, int64_t n_blocks, cudaStream_t st) {
+#define X(k)                                                                              \
+    if (prob->K == k) {                                                                   \
+        return prob->dtype == VLG_F32 ? launch_pass1<float, k>(warp, pp, n_blocks, st)    \
+                                      : launch_pass1<__nv_bfloat16, k>(warp, pp, n_blocks, st); \
+    }
+    VLG_FOR_EACH_K(X)
+#undef X
+    return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
+}
+
+template <typename T, int K>
+static int launch_pass2(const Pass2Params &pp, int64_t n_blocks, int64_t P, const vlg_problem_t *prob, size_t far_words, cudaStream_t st) {
+    if (pp.far_acc || (prob->flags & VLG_FLAG_NO_FAR_PATH)) {
+        far_zero_kernel<<<148 * 4, 256, 0, st>>>(pp.far_acc, (int64_t)far_words, pp.hdr, prob->flags, pp.hdr);
+        int rc = check_launch("far_zero_kernel");
+        if (rc) return rc;
+    }
+    if (pp.far_acc) {
+        far_scatter_kernel<K><<<148 * 8, 256, 0, st>>>(pp, P);
+        int rc = check_launch("far_scatter_kernel");
+        if (rc) return rc;
+    }
+    constexpr size_t smem = pass2_smem_bytes<K>();
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pass2_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass2): %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    pass2_kernel<T, K><<<(unsigned)n_blocks, kThreads, smem, st>>>(pp);
+    return check_launch("pass2_kernel");
+}
+
+template <typename T, int K>
+static int launch_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
+                      void *out_rgb, void *out_layout, int64_t *out_argmax, int32_t *dbg, cudaStream_t st) {
+    const int64_t HW = prob->H * prob->W, P = prob->N * HW;
+    warp_fwd_kernel<T, K><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
+        make_cc(prob), P, HW, (const T *)src_rgb, (const T *)src_layout, (const float2 *)coords, (T *)out_rgb,
+        (T *)out_layout, out_argmax, (int2 *)dbg);
+    return check_launch("warp_fwd_kernel");
+}
+
+static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, const void *src_layout,
+                     const float *coords, const void *tgt_rgb, const int64_t *tgt_label, float *d_coords,
+                     void *d_out_rgb, void *d_out_lay, bool need_grad, int64_t *out_argmax, void *workspace,
+                     const WsLayout &L, cudaStream_t st) {
+    char *ws = (char *)workspace;
+    WsHeader *hdr = (WsHeader *)(ws + L.header);
+    cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(WsHeader), st);
+    if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "memset header: %s", cudaGetErrorString(e));
+    const int64_t P = prob->N * prob->H * prob->W;
+    const bool has_lay = src_layout && tgt_label;
+    if (has_lay) {
+        const int blocks = (int)((P + 256 * 8 - 1) / (256 * 8));
+        count_valid_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(tgt_label, P, prob->ignore_index, hdr);
+        int rc = check_launch("count_valid_kernel");
+        if (rc) return rc;
+    }
+    const double Ng = (double)(prob->global_N ? prob->global_N : prob->N);
+    const double H = (double)prob->H, W = (double)prob->W;
+    Pass1Params pp{};
+    pp.cc = make_cc(prob);
+    pp.N = (int)prob->N;
+    pp.tiles_x = (int)tiles_x(prob->W);
+    pp.tiles_y = (int)tiles_y(prob->H);
+    pp.src_rgb = src_rgb; pp.src_layout = src_layout; pp.coords = coords;
+    pp.tgt_rgb = tgt_rgb; pp.label = tgt_label; pp.ignore_index = prob->ignore_index;
+    pp.c_l1 = (float)(prob->w_l1 / (Ng * 3 * H * W));
+    pp.c_gd = (float)(prob->w_gd / (Ng * 3 * H * W));
+    pp.c_ssim = (prob->H > 2 && prob->W > 2) ? (float)(prob->w_ssim / (2.0 * Ng * (H - 2) * (W - 2))) : 0.f;
+    pp.terms = prob->term_mask ? prob->term_mask : VLG_TERM_ALL;
+    if (!(prob->H > 2 && prob->W > 2)) pp.terms &= ~VLG_TERM_SSIM;
+    pp.do_tv = warp && prob->coord_mode == VLG_COORD_FLOW && (pp.terms & VLG_TERM_TV);
+    pp.c_tvh = prob->H > 1 ? (float)(prob->w_tv / (Ng * (H - 1) * W * 2)) : 0.f;
+    pp.c_tvw = prob->W > 1 ? (float)(prob->w_tv / (Ng * H * (W - 1) * 2)) : 0.f;
+    pp.w_ce_over_scale = (float)(prob->w_ce * (double)prob->N / Ng);
+    pp.need_grad = need_grad;
+    pp.d_coords = d_coords; pp.d_out_rgb = d_out_rgb; pp.d_out_lay = d_out_lay;
+    pp.out_argmax = out_argmax;
+    pp.partials = (float *)(ws + L.partials);
+    pp.hdr = hdr;
+    pp.flags = prob->flags;
+    return dispatch_pass1(prob, warp, pp, L.n_blocks, st);
+}
+
+// ------------------------------------------------------------------ exported C ABI
+extern "C" {
+
+int vlg_version(void) { return VLG_VERSION; }
+const char *vlg_last_error(void) { return g_err; }
+int64_t vlg_launch_count(void) { return g_launches.load(); }
+
+size_t vlg_workspace_bytes(const vlg_problem_t *prob, int with_src_grad) {
+    if (check_problem(prob)) return 0;
+    return ws_layout(prob, with_src_grad).total;
+}
+
+int vlg_warp_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
+                 void *out_rgb, void *out_layout, int64_t *out_argmax, int32_t *dbg_x0y0, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if (!coords) return fail(VLG_ERR_ARG, "coords is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+#define X(k)                                                                                                   \
+    if (prob->K == k)                                                                                          \
+        return prob->dtype == VLG_F32                                                                          \
+                   ? launch_fwd<float, k>(prob, src_rgb, src_layout, coords, out_rgb, out_layout, out_argmax, dbg_x0y0, st) \
+                   : launch_fwd<__nv_bfloat16, k>(prob, src_rgb, src_layout, coords, out_rgb, out_layout, out_argmax, dbg_x0y0, st);
+    VLG_FOR_EACH_K(X)
+#undef X
+    return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
+}
+
+int vlg_warp_loss_bwd_out(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
+                          const void *tgt_rgb, const int64_t *tgt_label, float *d_coords, int64_t *out_argmax,
+                          int with_src_grad, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if (!coords) return fail(VLG_ERR_ARG, "coords is NULL");
+    if (with_src_grad && !d_coords) return fail(VLG_ERR_ARG, "with_src_grad needs d_coords (gradient pass)");
+    const WsLayout L = ws_layout(prob, with_src_grad);
+    if (!workspace || workspace_bytes < L.total) return fail(VLG_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
+    char *ws = (char *)workspace;
+    return run_pass1(prob, true, src_rgb, src_layout, coords, tgt_rgb, tgt_label, d_coords,
+                     with_src_grad ? ws + L.dout_rgb : nullptr, with_src_grad ? ws + L.dout_lay : nullptr,
+                     d_coords != nullptr, out_argmax, workspace, L, (cudaStream_t)stream);
+}
+
+int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src_rgb, void *d_src_layout,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if (!coords) return fail(VLG_ERR_ARG, "coords is NULL");
+    const WsLayout L = ws_layout(prob, 1);
+    if (!workspace || workspace_bytes < L.total) return fail(VLG_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
+    char *ws = (char *)workspace;
+    Pass2Params pp{};
+    pp.cc = make_cc(prob);
+    pp.N = (int)prob->N; pp.tiles_x = (int)tiles_x(prob->W); pp.tiles_y = (int)tiles_y(prob->H);
+    pp.coords = coords;
+    pp.d_out_rgb = (const float *)(ws + L.dout_rgb);
+    pp.d_out_lay = (const float *)(ws + L.dout_lay);
+    pp.d_src_rgb = d_src_rgb; pp.d_src_lay = d_src_layout;
+    pp.far_acc = L.far_acc ? (long long *)(ws + L.far_acc) : nullptr;
+    pp.hdr = (WsHeader *)(ws + L.header);
+    pp.HW = prob->H * prob->W;
+    const int64_t P = prob->N * pp.HW;
+    const size_t far_words = (size_t)P * (3 + prob->K);
+    cudaStream_t st = (cudaStream_t)stream;
+#define X(k)                                                                                       \
+    if (prob->K == k)                                                                              \
+        return prob->dtype == VLG_F32 ? launch_pass2<float, k>(pp, L.n_blocks, P, prob, far_words, st) \
+                                      : launch_pass2<__nv_bfloat16, k>(pp, L.n_blocks, P, prob, far_words, st);
+    VLG_FOR_EACH_K(X)
+#undef X
+    return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
+}
+
+int vlg_reduce_partials(const vlg_problem_t *prob, float *loss_out, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if (!loss_out) return fail(VLG_ERR_ARG, "loss_out is NULL");
+    const WsLayout L = ws_layout(prob, 0);
+    if (!workspace || workspace_bytes < L.total) return fail(VLG_ERR_WORKSPACE, "workspace too small");
+    char *ws = (char *)workspace;
+    const double Ng = (double)(prob->global_N ? prob->global_N : prob->N);
+    const double H = (double)prob->H, W = (double)prob->W;
+    ReduceParams rp{};
+    rp.partials = (const float *)(ws + L.partials);
+    rp.n_blocks = L.n_blocks;
+    rp.hdr = (const WsHeader *)(ws + L.header);
+    rp.inv_numel_rgb = 1.0 / (Ng * 3 * H * W);
+    rp.inv_ssim = (prob->H > 2 && prob->W > 2) ? 1.0 / (Ng * (H - 2) * (W - 2)) : 0.0;
+    rp.inv_tvh = 1.0 / (Ng * (H - 1) * W * 2);
+    rp.inv_tvw = 1.0 / (Ng * H * (W - 1) * 2);
+    rp.ce_scale = (double)prob->N / Ng;
+    rp.w_l1 = prob->w_l1; rp.w_gd = prob->w_gd; rp.w_ssim = prob->w_ssim; rp.w_ce = prob->w_ce; rp.w_tv = prob->w_tv;
+    rp.out = loss_out;
+    reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rp);
+    return check_launch("reduce_partials_kernel");
+}
+
+int vlg_warp_loss_fwd_bwd(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
+                          const void *tgt_rgb, const int64_t *tgt_label, float *loss_out, float *d_coords,
+                          void *d_src_rgb, void *d_src_layout, int64_t *out_argmax, void *workspace,
+                          size_t workspace_bytes, void *stream) {
+    const int with_src = (d_src_rgb || d_src_layout) ? 1 : 0;
+    int rc = vlg_warp_loss_bwd_out(prob, src_rgb, src_layout, coords, tgt_rgb, tgt_label, d_coords, out_argmax,
+                                   with_src, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    if (loss_out) {
+        rc = vlg_reduce_partials(prob, loss_out, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+    }
+    if (with_src) rc = vlg_warp_bwd_src(prob, coords, d_src_rgb, d_src_layout, workspace, workspace_bytes, stream);
+    return rc;
+}
+
+int vlg_pixel_loss_fwd_bwd(const vlg_problem_t *prob, const void *out_rgb, const void *tgt_rgb, const void *logits,
+                           const int64_t *tgt_label, float *loss_out, void *d_out_rgb, void *d_logits,
+                           int64_t *out_argmax, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    const WsLayout L = ws_layout(prob, 0);
+    if (!workspace || workspace_bytes < L.total) return fail(VLG_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
+    if ((out_rgb == nullptr) != (tgt_rgb == nullptr)) return fail(VLG_ERR_ARG, "out_rgb and tgt_rgb go together");
+    if ((logits == nullptr) != (tgt_label == nullptr)) return fail(VLG_ERR_ARG, "logits and tgt_label go together");
+    rc = run_pass1(prob, false, out_rgb, logits, nullptr, tgt_rgb, tgt_label, nullptr, d_out_rgb, d_logits,
+                   d_out_rgb != nullptr || d_logits != nullptr, out_argmax, workspace, L, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (loss_out) rc = vlg_reduce_partials(prob, loss_out, workspace, workspace_bytes, stream);
+    return rc;
+}
+
+int vlg_scale_grads(void *g, int64_t n, int32_t dtype, const float *scale, void *stream) {
+    if (!g || !scale || n < 0) return fail(VLG_ERR_ARG, "bad arguments to vlg_scale_grads");
+    if (n == 0) return VLG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == VLG_F32) scale_kernel<float><<<148 * 8, 256, 0, st>>>((float *)g, n, scale);
+    else if (dtype == VLG_BF16) scale_kernel<__nv_bfloat16><<<148 * 8, 256, 0, st>>>((__nv_bfloat16 *)g, n, scale);
+    else return fail(VLG_ERR_ARG, "bad dtype");
+    return check_launch("scale_kernel");
+}
+
+int vlg_read_status(void *workspace, size_t workspace_bytes, uint32_t *host_status, void *stream) {
+    if (!workspace || workspace_bytes < sizeof(WsHeader) || !host_status) return fail(VLG_ERR_ARG, "bad arguments");
+    cudaError_t e = cudaMemcpyAsync(host_status, workspace, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "read status: %s", cudaGetErrorString(e));
+    return VLG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// vlg_device.cuh -- device-side building blocks shared by the sm_100a kernels.
+//
+// Coordinate arithmetic is written with explicit round-to-nearest intrinsics so that nvcc's FMA
+// contraction cannot change a single bit relative to the oracle:
+//   base grid   reference src/models/modules.py:69-70      arange(S)/(S-1)*2-1
+//   unnormalise torch ATen/native/GridSampler.h:31         ((g+1)/2)*(S-1)
+//   clip        GridSampler.h:58-60
+//   weights     Appendix A.5, accumulation Appendix A.6    fma(se, fma(sw, fma(ne, nw*)))
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vlg_b200.h"
+
+namespace vlg {
+
+// ---------------------------------------------------------------- workspace layout
+struct WsHeader {
+    uint32_t status;        // VLG_STATUS_* bits (sticky until the next pass-1 launch)
+    uint32_t maxdisp_bits;  // float bits of max |displacement| (non-negative => uint order == float order)
+    uint32_t maxgrad_bits;  // float bits of max |d_out| (scale of the fixed-point far path)
+    uint32_t far_count;     // number of far output pixels
+    unsigned long long n_valid;  // labels != ignore_index
+    uint32_t pad[26];
+};
+static_assert(sizeof(WsHeader) == 128, "header size");
+
+constexpr int kPartialSlots = 8;  // l1, gd, ssim, ce, tv_h, tv_w, n_valid(unused), spare
+
+struct WsLayout {
+    size_t header, partials, dout_rgb, dout_lay, far_acc, total;
+    int64_t n_blocks;
+};
+
+// ---------------------------------------------------------------- tiling of pass 1
+constexpr int kTW = 32, kTH = 8;          // output tile (one thread per pixel)
+constexpr int kHalo = 2;                  // SSIM adjoint reaches 2 pixels
+constexpr int kRW = kTW + 2 * kHalo, kRH = kTH + 2 * kHalo, kRN = kRW * kRH;  // rgb region
+constexpr int kWW = kTW + 2, kWH = kTH + 2, kWN = kWW * kWH;                  // 3x3 windows
+constexpr int kThreads = kTW * kTH;
+
+__host__ __device__ inline int64_t tiles_x(int64_t W) { return (W + kTW - 1) / kTW; }
+__host__ __device__ inline int64_t tiles_y(int64_t H) { return (H + kTH - 1) / kTH; }
+
+// ---------------------------------------------------------------- typed loads / stores
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__host__ __device__ constexpr int vec_bytes(int pixel_bytes) {
+    return pixel_bytes % 16 == 0 ? 16 : pixel_bytes % 8 == 0 ? 8 : pixel_bytes % 4 == 0 ? 4 : 2;
+}
+
+// Load C consecutive channels of one pixel (read-only path) into fp32 registers.
+template <typename T, int C>
+__device__ __forceinline__ void load_px(const T *__restrict__ p, float (&v)[C]) {
+    constexpr int VB = vec_bytes(C * (int)sizeof(T));
+    constexpr int EPV = VB / (int)sizeof(T);  // elements per vector
+    static_assert(EPV >= 1, "vector narrower than an element");
+    if constexpr (VB == 16) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+        for (int i = 0; i < C / EPV; ++i) {
+            uint4 r = __ldg(q + i);
+            const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) v[i * EPV + j] = to_f<T>(e[j]);
+        }
+    } else if constexpr (VB == 8) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+        for (int i = 0; i < C / EPV; ++i) {
+            uint2 r = __ldg(q + i);
+            const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) v[i * EPV + j] = to_f<T>(e[j]);
+        }
+    } else if constexpr (VB == 4 && sizeof(T) == 2) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+#pragma unroll
+        for (int i = 0; i < C / 2; ++i) {
+            uint32_t r = __ldg(q + i);
+            const T *e = reinterpret_cast<const T *>(&r);
+            v[2 * i] = to_f<T>(e[0]);
+            v[2 * i + 1] = to_f<T>(e[1]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i) v[i] = to_f<T>(__ldg(p + i));
+    }
+}
+
+template <typename T, int C>
+__device__ __forceinline__ void store_px(T *__restrict__ p, const float (&v)[C]) {
+    constexpr int VB = vec_bytes(C * (int)sizeof(T));
+    constexpr int EPV = VB / (int)sizeof(T);
+    if constexpr (VB == 16) {
+        uint4 *q = reinterpret_cast<uint4 *>(p);
+#pragma unroll
+        for (int i = 0; i < C / EPV; ++i) {
+            uint4 r;
+            T *e = reinterpret_cast<T *>(&r);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) e[j] = from_f<T>(v[i * EPV + j]);
+            q[i] = r;
+        }
+    } else if constexpr (VB == 8) {
+        uint2 *q = reinterpret_cast<uint2 *>(p);
+#pragma unroll
+        for (int i = 0; i < C / EPV; ++i) {
+            uint2 r;
+            T *e = reinterpret_cast<T *>(&r);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) e[j] = from_f<T>(v[i * EPV + j]);
+            q[i] = r;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i) p[i] = from_f<T>(v[i]);
+    }
+}
+
+// ---------------------------------------------------------------- sampling coordinates
+struct CoordCfg {
+    int H, W;
+    int padding, coord_mode;
+    float Wm1, Hm1;  // (float)(W-1), (float)(H-1)
+    float sx, sy;    // fp32(2/(W-1)), fp32(2/(H-1)) rounded once from double on the host
+};
+
+struct Taps {
+    float ix, iy;     // source coordinates after padding treatment
+    float fx0, fy0;   // floor
+    float nw, ne, sw, se;
+    int x0, y0;
+    float mx, my;     // d(ix)/d(coord) incl. border mask and (flow mode) the pixel->grid scale
+};
+
+__device__ __forceinline__ float base_coord(int i, float Sm1) {
+    // reference src/models/modules.py:69: (i / (S-1)) * 2 - 1, one rounding per op
+    return __fsub_rn(__fmul_rn(__fdiv_rn((float)i, Sm1), 2.0f), 1.0f);
+}
+
+// c = raw coords of output pixel (y,x): flow in pixels or normalised grid value.
+__device__ __forceinline__ Taps make_taps(const CoordCfg &cc, float2 c, int y, int x) {
+    float gx, gy;
+    if (cc.coord_mode == VLG_COORD_FLOW) {
+        gx = __fadd_rn(base_coord(x, cc.Wm1), __fmul_rn(c.x, cc.sx));
+        gy = __fadd_rn(base_coord(y, cc.Hm1), __fmul_rn(c.y, cc.sy));
+    } else {
+        gx = c.x;
+        gy = c.y;
+    }
+    // GridSampler.h:31 -- (g+1)/2 is exact, so one rounding after the add and one after the mul
+    float ux = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), cc.Wm1);
+    float uy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), cc.Hm1);
+    Taps t;
+    // GridSampler.h:47 and :70-81 (border positions count as clipped for the gradient)
+    t.mx = __fmul_rn(cc.Wm1, 0.5f);
+    t.my = __fmul_rn(cc.Hm1, 0.5f);
+    if (cc.padding == VLG_PAD_BORDER) {
+        if (ux <= 0.0f || ux >= cc.Wm1) t.mx = 0.0f;
+        if (uy <= 0.0f || uy >= cc.Hm1) t.my = 0.0f;
+        ux = fminf(cc.Wm1, fmaxf(ux, 0.0f));
+        uy = fminf(cc.Hm1, fmaxf(uy, 0.0f));
+    }
+    if (cc.coord_mode == VLG_COORD_FLOW) {
+        t.mx *= cc.sx;
+        t.my *= cc.sy;
+    }
+    t.ix = ux;
+    t.iy = uy;
+    t.fx0 = floorf(ux);
+    t.fy0 = floorf(uy);
+    const float fx1 = __fadd_rn(t.fx0, 1.0f), fy1 = __fadd_rn(t.fy0, 1.0f);
+    const float wx1 = __fsub_rn(ux, t.fx0), wx0 = __fsub_rn(fx1, ux);
+    const float wy1 = __fsub_rn(uy, t.fy0), wy0 = __fsub_rn(fy1, uy);
+    t.nw = __fmul_rn(wx0, wy0);
+    t.ne = __fmul_rn(wx1, wy0);
+    t.sw = __fmul_rn(wx0, wy1);
+    t.se = __fmul_rn(wx1, wy1);
+    // Saturating conversion keeps far-out-of-range zeros-mode coordinates harmless.
+    t.x0 = (int)fminf(fmaxf(t.fx0, -4.0f), (float)cc.W + 4.0f);
+    t.y0 = (int)fminf(fmaxf(t.fy0, -4.0f), (float)cc.H + 4.0f);
+    return t;
+}
+
+// Chebyshev displacement of the sampling position from its own output pixel, in source pixels.
+// Output pixels whose four taps all fall outside the image contribute nothing and report 0.
+__device__ __forceinline__ float tap_displacement(const CoordCfg &cc, const Taps &t, int y, int x) {
+    if (t.x0 < -1 || t.x0 >= cc.W || t.y0 < -1 || t.y0 >= cc.H) return 0.0f;
+    return fmaxf(fabsf(t.ix - (float)x), fabsf(t.iy - (float)y));
+}
+
+// Bilinear gather of C channels at one output pixel from an NHWC image plane `img` (batch n
+// already applied).  Bit-exact FMA chain of Appendix A.6; out-of-image taps read 0.
+template <typename T, int C>
+__device__ __forceinline__ void gather_px(const T *__restrict__ img, const CoordCfg &cc, const Taps &t,
+                                          float (&out)[C]) {
+    const bool xin0 = t.x0 >= 0 && t.x0 < cc.W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < cc.W;
+    const bool yin0 = t.y0 >= 0 && t.y0 < cc.H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < cc.H;
+    const T *p00 = img + ((int64_t)t.y0 * cc.W + t.x0) * C;
+    float v[C];
+    if (yin0 && xin0) {
+        load_px<T, C>(p00, v);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = __fmul_rn(v[c], t.nw);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = __fmul_rn(0.0f, t.nw);
+    }
+    if (yin0 && xin1) {
+        load_px<T, C>(p00 + C, v);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = __fmaf_rn(v[c], t.ne, out[c]);
+    }
+    if (yin1 && xin0) {
+        load_px<T, C>(p00 + (int64_t)cc.W * C, v);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = __fmaf_rn(v[c], t.sw, out[c]);
+    }
+    if (yin1 && xin1) {
+        load_px<T, C>(p00 + (int64_t)cc.W * C + C, v);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = __fmaf_rn(v[c], t.se, out[c]);
+    }
+}
+
+// d(out)/d(ix), d(out)/d(iy) contracted with the per-channel upstream gradient g[C]
+// (GridSampler.h backward: gix = sum_c g_c * [(v_ne-v_nw)(y1-iy) + (v_se-v_sw)(iy-y0)]).
+template <typename T, int C>
+__device__ __forceinline__ void coord_grad_px(const T *__restrict__ img, const CoordCfg &cc, const Taps &t,
+                                              const float (&g)[C], float &gix, float &giy) {
+    const bool xin0 = t.x0 >= 0 && t.x0 < cc.W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < cc.W;
+    const bool yin0 = t.y0 >= 0 && t.y0 < cc.H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < cc.H;
+    const T *p00 = img + ((int64_t)t.y0 * cc.W + t.x0) * C;
+    float a[C], b[C];  // a = sum_c g_c v_nw.. handled tap by tap to keep registers low
+    const float wx1 = t.ix - t.fx0, wx0 = (t.fx0 + 1.0f) - t.ix;
+    const float wy1 = t.iy - t.fy0, wy0 = (t.fy0 + 1.0f) - t.iy;
+    float dnw = 0.f, dne = 0.f, dsw = 0.f, dse = 0.f;  // sum_c g_c * v_tap
+    if (yin0 && xin0) {
+        load_px<T, C>(p00, a);
+#pragma unroll
+        for (int c = 0; c < C; ++c) dnw = fmaf(g[c], a[c], dnw);
+    }
+    if (yin0 && xin1) {
+        load_px<T, C>(p00 + C, b);
+#pragma unroll
+        for (int c = 0; c < C; ++c) dne = fmaf(g[c], b[c], dne);
+    }
+    if (yin1 && xin0) {
+        load_px<T, C>(p00 + (int64_t)cc.W * C, a);
+#pragma unroll
+        for (int c = 0; c < C; ++c) dsw = fmaf(g[c], a[c], dsw);
+    }
+    if (yin1 && xin1) {
+        load_px<T, C>(p00 + (int64_t)cc.W * C + C, b);
+#pragma unroll
+        for (int c = 0; c < C; ++c) dse = fmaf(g[c], b[c], dse);
+    }
+    gix += (dne - dnw) * wy0 + (dse - dsw) * wy1;
+    giy += (dsw - dnw) * wx0 + (dse - dne) * wx1;
+}
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float sgn(float v) { return (float)((v > 0.0f) - (v < 0.0f)); }
+
+}  // namespace vlg

@@ -1,0 +1,258 @@
+"""Torch-facing operators over the C ABI (include/vlg_b200.h).
+
+Everything here is plumbing: device memory comes from torch's allocator, the stream is torch's
+current stream, the arithmetic happens in libvlg_b200.so.  There is NO CPU / eager fallback: a
+non-CUDA tensor or a missing library raises.
+
+Call signatures mirror the reference's: image tensors are NCHW-logical
+(`[N,3,H,W]`, `[N,K,H,W]`), labels int64 `[N,H,W]` (src/folder.py:100).  Tensors already in
+`torch.channels_last` storage are consumed in place; NCHW-contiguous ones get ONE explicit
+permute-copy.  `flow` / `grid` are `[N,H,W,2]` fp32 (x first), i.e. the channels_last storage of a
+`[N,2,H,W]` flow head.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import Problem, VlgError, check
+
+_DTYPES = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+_PADDING = {"zeros": _cabi.PAD_ZEROS, "border": _cabi.PAD_BORDER}
+
+
+@dataclass
+class WarpLossConfig:
+    """Weights follow src/trainer.py:248-250 (40*L1 + 20*(GD+SSIM) + 10*CE); w_tv is new."""
+    w_l1: float = 40.0
+    w_gd: float = 20.0
+    w_ssim: float = 20.0
+    w_ce: float = 10.0
+    w_tv: float = 0.0
+    padding_mode: str = "border"          # oracle default
+    coords_are_grid: bool = False         # False: pixel flow; True: normalised sampling grid
+    ignore_index: int = -100              # nn.CrossEntropyLoss default (src/trainer.py:124)
+    global_batch: int = 0                 # data-parallel: divisor batch (0 = local batch)
+    assume_near: bool = False             # caller asserts |flow| < NEAR_RADIUS: skip far-path launches
+    term_mask: int = 0                    # 0 = all terms
+    want_argmax: bool = False
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise VlgError("video-layout-generation_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
+def _nhwc_strides(shape):
+    N, Cc, H, W = shape
+    return (H * W * Cc, 1, W * Cc, Cc)
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Return `x` (NCHW-logical) backed by dense NHWC storage; no copy if it already is."""
+    if x.dim() != 4:
+        raise VlgError(f"expected a 4-d NCHW-logical tensor, got shape {tuple(x.shape)}")
+    want = _nhwc_strides(x.shape)
+    ok = all(x.shape[d] == 1 or x.stride(d) == want[d] for d in range(4))
+    if ok and x.data_ptr() % 16 == 0:
+        return x
+    y = torch.empty_strided(x.shape, want, dtype=x.dtype, device=x.device)
+    y.copy_(x)
+    return y
+
+
+def empty_nhwc(shape, dtype, device) -> torch.Tensor:
+    return torch.empty_strided(tuple(shape), _nhwc_strides(shape), dtype=dtype, device=device)
+
+
+def _coords(c: torch.Tensor, N, H, W) -> torch.Tensor:
+    if c.dtype != torch.float32:
+        raise VlgError("flow / grid must be float32 (bf16 cannot address 2048 columns)")
+    if tuple(c.shape) != (N, H, W, 2):
+        raise VlgError(f"flow / grid must be [N,H,W,2]={N, H, W, 2}, got {tuple(c.shape)}")
+    return c.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
+    if dtype not in _DTYPES:
+        raise VlgError(f"unsupported activation dtype {dtype}; use float32 or bfloat16")
+    flags = _cabi.FLAG_NO_FAR_PATH if cfg.assume_near else 0
+    return Problem(N=N, H=H, W=W, K=K, dtype=_DTYPES[dtype], padding=_PADDING[cfg.padding_mode],
+                   coord_mode=_cabi.COORD_GRID if cfg.coords_are_grid else _cabi.COORD_FLOW, flags=flags,
+                   ignore_index=cfg.ignore_index, w_l1=cfg.w_l1, w_gd=cfg.w_gd, w_ssim=cfg.w_ssim,
+                   w_ce=cfg.w_ce, w_tv=cfg.w_tv, term_mask=cfg.term_mask, reserved=0,
+                   global_N=cfg.global_batch)
+
+
+def _workspace(prob: Problem, with_src: bool, device) -> torch.Tensor:
+    lib = _cabi.load()
+    n = lib.vlg_workspace_bytes(C.byref(prob), int(with_src))
+    if n == 0:
+        raise VlgError(lib.vlg_last_error().decode())
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------- forward-only warp
+@torch.no_grad()
+def warp(src_rgb: Optional[torch.Tensor], src_layout: Optional[torch.Tensor], coords: torch.Tensor, *,
+         padding_mode: str = "border", coords_are_grid: bool = False, want_layout: bool = True,
+         want_argmax: bool = True, debug_indices: bool = False):
+    """Validation / rollout warp (src/trainer.py:329-342,460-469).  Returns
+    (warped_rgb | None, warped_layout | None, argmax | None[, x0y0 int32])."""
+    lib = _cabi.load()
+    _require_cuda(src_rgb, src_layout, coords)
+    ref = src_rgb if src_rgb is not None else src_layout
+    if ref is None:
+        raise VlgError("warp needs at least one source tensor")
+    N, _, H, W = ref.shape
+    K = src_layout.shape[1] if src_layout is not None else 20
+    cfg = WarpLossConfig(padding_mode=padding_mode, coords_are_grid=coords_are_grid)
+    prob = _problem(N, H, W, K, ref.dtype, cfg)
+    coords = _coords(coords, N, H, W)
+    dev = ref.device
+    a = to_nhwc(src_rgb) if src_rgb is not None else None
+    b = to_nhwc(src_layout) if src_layout is not None else None
+    out_rgb = empty_nhwc((N, 3, H, W), ref.dtype, dev) if a is not None else None
+    out_lay = empty_nhwc((N, K, H, W), ref.dtype, dev) if (b is not None and want_layout) else None
+    out_arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if (b is not None and want_argmax) else None
+    dbg = torch.empty((N, H, W, 2), dtype=torch.int32, device=dev) if debug_indices else None
+    check(lib.vlg_warp_fwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(coords), _ptr(out_rgb), _ptr(out_lay),
+                           _ptr(out_arg), _ptr(dbg), _stream()))
+    res = (out_rgb, out_lay, out_arg)
+    return res + (dbg,) if debug_indices else res
+
+
+# --------------------------------------------------------------------------- fused warp + loss
+class _WarpLossFn(torch.autograd.Function):
+    """Fused forward+backward: the gradients are produced by the SAME pass as the losses (for an
+    upstream gradient of 1) and rescaled on the device in backward() only if it differs from 1."""
+
+    @staticmethod
+    def forward(ctx, src_rgb, src_layout, coords, tgt_rgb, tgt_label, cfg: WarpLossConfig):
+        lib = _cabi.load()
+        _require_cuda(src_rgb, src_layout, coords, tgt_rgb, tgt_label)
+        N, _, H, W = src_rgb.shape
+        K = src_layout.shape[1]
+        dev, dt = src_rgb.device, src_rgb.dtype
+        if src_layout.dtype != dt or tgt_rgb.dtype != dt:
+            raise VlgError("src_rgb, src_layout and tgt_rgb must share one dtype")
+        if tgt_label.dtype != torch.int64 or tuple(tgt_label.shape) != (N, H, W):
+            raise VlgError("tgt_label must be int64 [N,H,W] (src/folder.py:100)")
+        prob = _problem(N, H, W, K, dt, cfg)
+        need_c, need_a, need_b = ctx.needs_input_grad[2], ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_src = need_a or need_b
+        need_any = need_c or need_src
+        a, b, t = to_nhwc(src_rgb), to_nhwc(src_layout), to_nhwc(tgt_rgb)
+        c = _coords(coords, N, H, W)
+        lab = tgt_label.contiguous()
+        ws = _workspace(prob, need_src, dev)
+        loss = torch.empty(_cabi.LOSS_SLOTS, dtype=torch.float32, device=dev)
+        d_c = torch.empty_like(c) if need_any else None
+        d_a = empty_nhwc(a.shape, dt, dev) if need_src else None
+        d_b = empty_nhwc(b.shape, dt, dev) if need_src else None
+        arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if cfg.want_argmax else None
+        check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(c), _ptr(t), _ptr(lab), _ptr(loss),
+                                        _ptr(d_c), _ptr(d_a), _ptr(d_b), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
+        ctx.grads = (d_a if need_a else None, d_b if need_b else None, d_c if need_c else None)
+        ctx.consumed = False
+        ctx.workspace = ws  # holds the status word; freed with the graph
+        total = loss[_cabi.LOSS_TOTAL]
+        ctx.mark_non_differentiable(loss)
+        if arg is not None:
+            ctx.mark_non_differentiable(arg)
+            return total, loss, arg
+        return total, loss, None
+
+    @staticmethod
+    def backward(ctx, g_total, g_loss, g_arg):
+        if ctx.consumed:
+            raise VlgError("the fused warp-loss gradients were already consumed (retain_graph is unsupported)")
+        ctx.consumed = True
+        lib = _cabi.load()
+        d_a, d_b, d_c = ctx.grads
+        g = g_total.detach().to(torch.float32).contiguous()
+        for t in (d_a, d_b, d_c):
+            if t is not None:
+                check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
+        return d_a, d_b, d_c, None, None, None
+
+
+def warp_loss(src_rgb, src_layout, coords, tgt_rgb, tgt_label, cfg: Optional[WarpLossConfig] = None):
+    """Returns (total, loss_vector[LOSS_SLOTS], argmax | None).  `total` is differentiable w.r.t.
+    coords (flow / grid), src_rgb and src_layout."""
+    return _WarpLossFn.apply(src_rgb, src_layout, coords, tgt_rgb, tgt_label, cfg or WarpLossConfig())
+
+
+# --------------------------------------------------------------------------- reference call sites
+class _PixelLossFn(torch.autograd.Function):
+    """The reference's own criteria (no warp): L1 / GradientLoss / SsimLoss on (output, target),
+    cross-entropy on (input, target) -- src/trainer.py:248-250, src/loss.py:16-25,64-91."""
+
+    @staticmethod
+    def forward(ctx, out_rgb, tgt_rgb, logits, tgt_label, cfg: WarpLossConfig):
+        lib = _cabi.load()
+        _require_cuda(out_rgb, tgt_rgb, logits, tgt_label)
+        ref = out_rgb if out_rgb is not None else logits
+        N, _, H, W = ref.shape
+        K = logits.shape[1] if logits is not None else 20
+        dev, dt = ref.device, ref.dtype
+        prob = _problem(N, H, W, K, dt, cfg)
+        need_a = out_rgb is not None and ctx.needs_input_grad[0]
+        need_z = logits is not None and ctx.needs_input_grad[2]
+        a = to_nhwc(out_rgb) if out_rgb is not None else None
+        t = to_nhwc(tgt_rgb.to(dt)) if tgt_rgb is not None else None
+        z = to_nhwc(logits) if logits is not None else None
+        lab = tgt_label.contiguous() if tgt_label is not None else None
+        if lab is not None and (lab.dtype != torch.int64 or tuple(lab.shape) != (N, H, W)):
+            raise VlgError("target labels must be int64 [N,H,W]")
+        ws = _workspace(prob, False, dev)
+        loss = torch.empty(_cabi.LOSS_SLOTS, dtype=torch.float32, device=dev)
+        d_a = empty_nhwc(a.shape, dt, dev) if need_a else None
+        d_z = empty_nhwc(z.shape, dt, dev) if need_z else None
+        arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if (cfg.want_argmax and z is not None) else None
+        check(lib.vlg_pixel_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(t), _ptr(z), _ptr(lab), _ptr(loss), _ptr(d_a),
+                                         _ptr(d_z), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
+        ctx.grads = (d_a, d_z)
+        ctx.consumed = False
+        ctx.mark_non_differentiable(loss)
+        if arg is not None:
+            ctx.mark_non_differentiable(arg)
+        return loss[_cabi.LOSS_TOTAL], loss, arg
+
+    @staticmethod
+    def backward(ctx, g_total, g_loss, g_arg):
+        if ctx.consumed:
+            raise VlgError("the fused pixel-loss gradients were already consumed (retain_graph is unsupported)")
+        ctx.consumed = True
+        lib = _cabi.load()
+        d_a, d_z = ctx.grads
+        g = g_total.detach().to(torch.float32).contiguous()
+        for t in (d_a, d_z):
+            if t is not None:
+                check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
+        return d_a, None, d_z, None, None
+
+
+def pixel_losses(out_rgb, tgt_rgb, logits, tgt_label, cfg: Optional[WarpLossConfig] = None):
+    """Returns (total, loss_vector, argmax | None) for the reference's un-warped loss call sites."""
+    return _PixelLossFn.apply(out_rgb, tgt_rgb, logits, tgt_label, cfg or WarpLossConfig())
+
+
+def read_status(workspace: torch.Tensor) -> int:
+    """Synchronising debug helper: VLG_STATUS_* bits left by the last pass on this workspace."""
+    st = C.c_uint32(0)
+    check(_cabi.load().vlg_read_status(_ptr(workspace), workspace.numel(), C.byref(st), _stream()))
+    return st.value
