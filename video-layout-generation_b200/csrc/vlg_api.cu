@@ -2,6 +2,7 @@
 // kernel launches.  No allocation, no host synchronisation (except vlg_read_status), no torch.
 #include <atomic>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 
@@ -60,6 +61,7 @@ static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
     size_t off = 0;
     L.header = off; off = align_up(off + sizeof(WsHeader), 256);
     L.partials = off; off = align_up(off + (size_t)L.n_blocks * kPartialSlots * sizeof(float), 256);
+    L.tile_disp = off; off = align_up(off + (size_t)L.n_blocks * sizeof(float), 256);
     L.dout_rgb = L.dout_lay = L.far_acc = 0;
     if (with_src_grad) {
         L.dout_rgb = off; off = align_up(off + P * 3 * sizeof(float), 256);
@@ -194,8 +196,19 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, i
 // ------------------------------------------------------------------ dispatch helpers
 template <typename T, int K>
 static int launch_pass1(bool warp, const Pass1Params &pp, int64_t n_blocks, cudaStream_t st) {
-    if (warp) pass1_kernel<T, K, true><<<(unsigned)n_blocks, kThreads, 0, st>>>(pp);
-    else pass1_kernel<T, K, false><<<(unsigned)n_blocks, kThreads, 0, st>>>(pp);
+    // the staged source window is the last member: the un-warped criteria do not allocate it
+    using Smem = Pass1Smem<T, K>;
+    const size_t smem_warp = sizeof(Smem), smem_plain = offsetof(Smem, stage);
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pass1_kernel<T, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(pass1_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
+        if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass1): %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    if (warp) pass1_kernel<T, K, true><<<(unsigned)n_blocks, kThreads, smem_warp, st>>>(pp);
+    else pass1_kernel<T, K, false><<<(unsigned)n_blocks, kThreads, smem_plain, st>>>(pp);
     return check_launch("pass1_kernel");
 }
 
@@ -281,6 +294,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.d_coords = d_coords; pp.d_out_rgb = d_out_rgb; pp.d_out_lay = d_out_lay;
     pp.out_argmax = out_argmax;
     pp.partials = (float *)(ws + L.partials);
+    pp.tile_disp = (float *)(ws + L.tile_disp);
     pp.hdr = hdr;
     pp.flags = prob->flags;
     return dispatch_pass1(prob, warp, pp, L.n_blocks, st);
@@ -346,6 +360,7 @@ int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src
     pp.d_src_rgb = d_src_rgb; pp.d_src_lay = d_src_layout;
     pp.far_acc = L.far_acc ? (long long *)(ws + L.far_acc) : nullptr;
     pp.hdr = (WsHeader *)(ws + L.header);
+    pp.tile_disp = (const float *)(ws + L.tile_disp);
     pp.HW = prob->H * prob->W;
     const int64_t P = prob->N * pp.HW;
     const size_t far_words = (size_t)P * (3 + prob->K);

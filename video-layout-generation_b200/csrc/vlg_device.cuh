@@ -29,7 +29,7 @@ static_assert(sizeof(WsHeader) == 128, "header size");
 constexpr int kPartialSlots = 8;  // l1, gd, ssim, ce, tv_h, tv_w, n_valid(unused), spare
 
 struct WsLayout {
-    size_t header, partials, dout_rgb, dout_lay, far_acc, total;
+    size_t header, partials, tile_disp, dout_rgb, dout_lay, far_acc, total;
     int64_t n_blocks;
 };
 
@@ -262,6 +262,57 @@ __device__ __forceinline__ void coord_grad_px(const T *__restrict__ img, const C
 #pragma unroll
         for (int c = 0; c < C; ++c) dse = fmaf(g[c], b[c], dse);
     }
+    gix += (dne - dnw) * wy0 + (dse - dsw) * wy1;
+    giy += (dsw - dnw) * wx0 + (dse - dne) * wx1;
+}
+
+// Shared-memory variants (plain loads, no read-only path) used on the staged source window.
+template <typename T, int C>
+__device__ __forceinline__ void load_px_smem(const T *p, float (&v)[C]) {
+    constexpr int VB = vec_bytes(C * (int)sizeof(T));
+    constexpr int EPV = VB / (int)sizeof(T);
+    if constexpr (VB == 16) {
+#pragma unroll
+        for (int i = 0; i < C / EPV; ++i) {
+            const uint4 r = reinterpret_cast<const uint4 *>(p)[i];
+            const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) v[i * EPV + j] = to_f<T>(e[j]);
+        }
+    } else if constexpr (VB == 8) {
+#pragma unroll
+        for (int i = 0; i < C / EPV; ++i) {
+            const uint2 r = reinterpret_cast<const uint2 *>(p)[i];
+            const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) v[i * EPV + j] = to_f<T>(e[j]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i) v[i] = to_f<T>(p[i]);
+    }
+}
+
+// coord_grad_px on a staged window: all four taps are present (out-of-image cells hold zeros).
+template <typename T, int C>
+__device__ __forceinline__ void coord_grad_smem(const T *p00, int row_stride, const Taps &t, const float (&g)[C],
+                                                float &gix, float &giy) {
+    const float wx1 = t.ix - t.fx0, wx0 = (t.fx0 + 1.0f) - t.ix;
+    const float wy1 = t.iy - t.fy0, wy0 = (t.fy0 + 1.0f) - t.iy;
+    float v[C];
+    float dnw = 0.f, dne = 0.f, dsw = 0.f, dse = 0.f;
+    load_px_smem<T, C>(p00, v);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dnw = fmaf(g[c], v[c], dnw);
+    load_px_smem<T, C>(p00 + C, v);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dne = fmaf(g[c], v[c], dne);
+    load_px_smem<T, C>(p00 + row_stride, v);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dsw = fmaf(g[c], v[c], dsw);
+    load_px_smem<T, C>(p00 + row_stride + C, v);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dse = fmaf(g[c], v[c], dse);
     gix += (dne - dnw) * wy0 + (dse - dsw) * wy1;
     giy += (dsw - dnw) * wx0 + (dse - dne) * wx1;
 }

@@ -8,7 +8,17 @@
 //                                           clamp((1-SSIM)/2,0,1).mean() summed over channels
 //   CE          src/trainer.py:124,250      mean over labels != ignore_index of -log_softmax[label]
 //   TV          (absent upstream)           mean|d_H flow| + mean|d_W flow|, stencils of loss.py:22,24
-//   composition src/trainer.py:248-251      w_l1*L1 + w_style*(GD+SSIM) + w_ce*CE (+ w_tv*TV)
+//   composition src/trainer.py:248-251      w_l1*L1 + w_gd*GD + w_ssim*SSIM + w_ce*CE (+ w_tv*TV)
+//
+// Phases of one CTA (256 threads, tile 32x8, rgb halo 2):
+//   0a  base-grid coordinates of the tile's rows/columns -> smem (one IEEE division each)
+//   0b  rgb over tile+halo: sampling coordinates, 4-tap gather of src_rgb, target -> smem;
+//       bounding box of the layout taps of the tile's own pixels (integer smem atomics)
+//   1   cp.async the source-layout bounding box into smem (zero-filled outside the image), and
+//       meanwhile evaluate the 3x3 SSIM windows (runs of 5 windows share their column sums)
+//   2   own pixel: L1 / GD / SSIM-adjoint, layout gather from smem, argmax, softmax-CE,
+//       coordinate gradient, TV, stores
+//   3   block reduction -> one row of partial sums, per-tile displacement maxima
 #pragma once
 #include "vlg_device.cuh"
 
@@ -35,24 +45,93 @@ struct Pass1Params {
     void *d_out_lay;
     int64_t *out_argmax;    // nullable
     float *partials;        // [n_blocks][kPartialSlots]
+    float *tile_disp;       // [n_blocks] max displacement among the tile's NEAR output pixels (WARP)
     WsHeader *hdr;
     uint32_t flags;
 };
 
-struct __align__(16) Pass1Smem {
-    float a[3][kRN];        // warped (or given) rgb over the tile + halo 2
-    float b[3][kRN];        // target rgb
-    float k[3][3][kWN];     // per-window SSIM adjoint coefficients (A,B,C) x channel
+// staged source-layout window (pixels); covers the tile's taps for displacement spreads up to
+// +-3 px horizontally and +-1 px vertically around the tile's mean motion
+constexpr int kSW = 40, kSH = 12;
+constexpr int kSegW = 5;                               // SSIM windows per run
+constexpr int kSegs = (kWW + kSegW - 1) / kSegW;       // 7 runs per window row
+static_assert(kSegs * kWH * 3 <= kThreads, "one SSIM run per thread");
+
+template <typename T, int K>
+struct Pass1Smem {
+    float2 ab[3][kRN];      // (warped-or-given rgb, target rgb) over the tile + halo 2
+    float2 flow[kRN];       // raw coords (TV stencil)
+    float4 k[3][kWN];       // per-window SSIM adjoint coefficients (A,B,C,-)
+    float bx[kRW], by[kRH]; // base-grid coordinates of the region's columns / rows
     float red[kThreads / 32][kPartialSlots];
-    float redmax[kThreads / 32][2];
+    float redmax[kThreads / 32][4];
+    int bbox[4];            // min x0, min y0, max x0, max y0 of the tile's own taps
+    alignas(16) T stage[kSH * kSW * K];
 };
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// sampling coordinates from raw coords + the smem base-grid table
+__device__ __forceinline__ float2 source_xy(const CoordCfg &cc, float2 c, float bx, float by, float &mx, float &my) {
+    float gx = c.x, gy = c.y;
+    if (cc.coord_mode == VLG_COORD_FLOW) {
+        gx = __fadd_rn(bx, __fmul_rn(c.x, cc.sx));
+        gy = __fadd_rn(by, __fmul_rn(c.y, cc.sy));
+    }
+    float ux = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), cc.Wm1);
+    float uy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), cc.Hm1);
+    mx = __fmul_rn(cc.Wm1, 0.5f);
+    my = __fmul_rn(cc.Hm1, 0.5f);
+    if (cc.padding == VLG_PAD_BORDER) {
+        if (ux <= 0.0f || ux >= cc.Wm1) mx = 0.0f;
+        if (uy <= 0.0f || uy >= cc.Hm1) my = 0.0f;
+        ux = fminf(cc.Wm1, fmaxf(ux, 0.0f));
+        uy = fminf(cc.Hm1, fmaxf(uy, 0.0f));
+    }
+    if (cc.coord_mode == VLG_COORD_FLOW) {
+        mx *= cc.sx;
+        my *= cc.sy;
+    }
+    return make_float2(ux, uy);
+}
+
+__device__ __forceinline__ Taps taps_from_xy(const CoordCfg &cc, float2 xy, float mx, float my) {
+    Taps t;
+    t.ix = xy.x; t.iy = xy.y; t.mx = mx; t.my = my;
+    t.fx0 = floorf(xy.x);
+    t.fy0 = floorf(xy.y);
+    const float fx1 = __fadd_rn(t.fx0, 1.0f), fy1 = __fadd_rn(t.fy0, 1.0f);
+    const float wx1 = __fsub_rn(xy.x, t.fx0), wx0 = __fsub_rn(fx1, xy.x);
+    const float wy1 = __fsub_rn(xy.y, t.fy0), wy0 = __fsub_rn(fy1, xy.y);
+    t.nw = __fmul_rn(wx0, wy0);
+    t.ne = __fmul_rn(wx1, wy0);
+    t.sw = __fmul_rn(wx0, wy1);
+    t.se = __fmul_rn(wx1, wy1);
+    t.x0 = (int)fminf(fmaxf(t.fx0, -4.0f), (float)cc.W + 4.0f);
+    t.y0 = (int)fminf(fmaxf(t.fy0, -4.0f), (float)cc.H + 4.0f);
+    return t;
+}
+
+// +-c with the sign of (u*v), 0 if either is 0  (c >= 0)
+__device__ __forceinline__ float signed_c(float c, float u, float v) {
+    const unsigned s = (__float_as_uint(u) ^ __float_as_uint(v)) & 0x80000000u;
+    return (u == 0.0f || v == 0.0f) ? 0.0f : __uint_as_float(__float_as_uint(c) | s);
+}
 
 template <typename T, int K, bool WARP>
 __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
-    __shared__ Pass1Smem sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Pass1Smem<T, K> &sm = *reinterpret_cast<Pass1Smem<T, K> *>(smem_raw);
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
     const int bt = blockIdx.x;
     const int n = bt / (p.tiles_x * p.tiles_y);
     const int trem = bt - n * (p.tiles_x * p.tiles_y);
@@ -67,82 +146,162 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
     const float2 *coords = WARP ? reinterpret_cast<const float2 *>(p.coords) + img_px : nullptr;
 
     float s_l1 = 0.f, s_gd = 0.f, s_ssim = 0.f, s_ce = 0.f, s_tvh = 0.f, s_tvw = 0.f;
-    float m_disp = 0.f, m_grad = 0.f;
+    float m_disp = 0.f, m_near = 0.f, m_grad = 0.f;
 
-    // ---------------- phase 0: rgb over the tile + halo ----------------
-    if (has_rgb) {
+    // ---------------- phase 0a: base grid of the region's rows / columns ----------------
+    if (WARP) {
+        if (tid < kRW) sm.bx[tid] = base_coord(tx0 - kHalo + tid, cc.Wm1);
+        else if (tid >= 64 && tid < 64 + kRH) sm.by[tid - 64] = base_coord(ty0 - kHalo + tid - 64, cc.Hm1);
+        if (tid == 128) { sm.bbox[0] = 1 << 30; sm.bbox[1] = 1 << 30; sm.bbox[2] = -(1 << 30); sm.bbox[3] = -(1 << 30); }
+        __syncthreads();
+    }
+
+    // ---------------- phase 0b: coordinates + rgb over the tile + halo ----------------
+    {
+        int bx0 = 1 << 30, by0 = 1 << 30, bx1 = -(1 << 30), by1 = -(1 << 30);
         for (int q = tid; q < kRN; q += kThreads) {
             const int ry = q / kRW, rx = q - ry * kRW;
             const int y = ty0 - kHalo + ry, x = tx0 - kHalo + rx;
             float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
+            float2 xy = make_float2(0.f, 0.f), fl = make_float2(0.f, 0.f);
             if (y >= 0 && y < H && x >= 0 && x < W) {
                 const int64_t o = (int64_t)y * W + x;
                 if (WARP) {
-                    const Taps t = make_taps(cc, __ldg(coords + o), y, x);
-                    gather_px<T, 3>(src_rgb, cc, t, a);
-                } else {
+                    float mx, my;
+                    fl = __ldg(coords + o);
+                    xy = source_xy(cc, fl, sm.bx[rx], sm.by[ry], mx, my);
+                    if (has_rgb) {
+                        const Taps t = taps_from_xy(cc, xy, mx, my);
+                        gather_px<T, 3>(src_rgb, cc, t, a);
+                    }
+                    const bool own = ry >= kHalo && ry < kHalo + kTH && rx >= kHalo && rx < kHalo + kTW;
+                    if (own && has_lay) {
+                        const int x0 = (int)fminf(fmaxf(floorf(xy.x), -4.0f), (float)W + 4.0f);
+                        const int y0 = (int)fminf(fmaxf(floorf(xy.y), -4.0f), (float)H + 4.0f);
+                        bx0 = min(bx0, x0); bx1 = max(bx1, x0);
+                        by0 = min(by0, y0); by1 = max(by1, y0);
+                    }
+                } else if (has_rgb) {
                     load_px<T, 3>(src_rgb + o * 3, a);
                 }
-                load_px<T, 3>(tgt_rgb + o * 3, b);
+                if (has_rgb) load_px<T, 3>(tgt_rgb + o * 3, b);
             }
+            if (has_rgb) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                sm.a[c][q] = a[c];
-                sm.b[c][q] = b[c];
+                for (int c = 0; c < 3; ++c) sm.ab[c][q] = make_float2(a[c], b[c]);
             }
+            if (WARP) sm.flow[q] = fl;
         }
-        __syncthreads();
-
-        // ---------------- phase 1: SSIM windows (top-left anchored) ----------------
-        if (p.terms & VLG_TERM_SSIM)
-        for (int w = tid; w < kWN; w += kThreads) {
-            const int wy = w / kWW, wx = w - wy * kWW;
-            const int i = ty0 - kHalo + wy, j = tx0 - kHalo + wx;  // top-left pixel of the window
-            const bool valid = i >= 0 && j >= 0 && i + 2 < H && j + 2 < W;
-            const bool own = valid && wy >= kHalo && wx >= kHalo;  // top-left inside this tile
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float kA = 0.f, kB = 0.f, kC = 0.f;
-                if (valid) {
-                    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
-#pragma unroll
-                    for (int di = 0; di < 3; ++di)
-#pragma unroll
-                        for (int dj = 0; dj < 3; ++dj) {
-                            const float xa = sm.a[c][(wy + di) * kRW + wx + dj];
-                            const float yb = sm.b[c][(wy + di) * kRW + wx + dj];
-                            sx += xa;
-                            sy += yb;
-                            sxx = fmaf(xa, xa, sxx);
-                            syy = fmaf(yb, yb, syy);
-                            sxy = fmaf(xa, yb, sxy);
-                        }
-                    const float C1 = 1e-4f, C2 = 9e-4f, inv9 = 1.0f / 9.0f;
-                    const float mx = sx * inv9, my = sy * inv9;
-                    const float vx = sxx * inv9 - mx * mx, vy = syy * inv9 - my * my;
-                    const float vxy = sxy * inv9 - mx * my;
-                    const float n1 = 2.f * mx * my + C1, n2 = 2.f * vxy + C2;
-                    const float d1 = mx * mx + my * my + C1, d2 = vx + vy + C2;
-                    const float inv_d1 = 1.0f / d1, inv_d2 = 1.0f / d2;
-                    const float S = (n1 * n2) * (inv_d1 * inv_d2);
-                    const float v = (1.0f - S) * 0.5f;
-                    if (own) s_ssim += fminf(1.0f, fmaxf(0.0f, v));
-                    if (p.need_grad && v >= 0.0f && v <= 1.0f) {
-                        // dS/dx_p = A + B x_p + C y_p; loss = (1-S)/2 / M
-                        const float r = inv_d1 * inv_d2;
-                        const float kk = -p.c_ssim * (2.0f / 9.0f);
-                        kB = kk * (-S * inv_d2);
-                        kC = kk * (n1 * r);
-                        kA = kk * (my * n2 * r - my * n1 * r - S * mx * inv_d1 + S * mx * inv_d2);
-                    }
-                }
-                sm.k[c][0][w] = kA;
-                sm.k[c][1][w] = kB;
-                sm.k[c][2][w] = kC;
+        if (WARP && has_lay) {
+            bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+            bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+            if (lane == 0) {
+                atomicMin(&sm.bbox[0], bx0); atomicMin(&sm.bbox[1], by0);
+                atomicMax(&sm.bbox[2], bx1); atomicMax(&sm.bbox[3], by1);
             }
         }
         __syncthreads();
     }
+
+    // ---------------- phase 1a: stage the source-layout window (async) ----------------
+    // window origin = min tap; extent clipped to the stage capacity.  Cells outside the image are
+    // zero-filled, so in-window taps need no bounds predicate (torch skips out-of-image taps).
+    int ox = 0, oy = 0, sw = 0, sh = 0;
+    if (WARP && has_lay) {
+        ox = sm.bbox[0]; oy = sm.bbox[1];
+        sw = min(kSW, sm.bbox[2] + 2 - ox);
+        sh = min(kSH, sm.bbox[3] + 2 - oy);
+        constexpr int VB = vec_bytes(K * (int)sizeof(T)) ;
+        constexpr int PXB = K * (int)sizeof(T);
+        if constexpr (VB == 16) {
+            constexpr int VPP = PXB / 16;
+            const int nvec = sw > 0 && sh > 0 ? sw * sh * VPP : 0;
+            for (int i = tid; i < nvec; i += kThreads) {
+                const int cell = i / VPP, v = i - cell * VPP;
+                const int ry = cell / sw, rx = cell - ry * sw;
+                const int y = oy + ry, x = ox + rx;
+                char *dst = reinterpret_cast<char *>(sm.stage) + ((size_t)(ry * kSW + rx) * PXB + v * 16);
+                if (y >= 0 && y < H && x >= 0 && x < W)
+                    cp_async16(dst, reinterpret_cast<const char *>(src_lay) + ((int64_t)y * W + x) * PXB + v * 16);
+                else
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+            const int nel = sw > 0 && sh > 0 ? sw * sh * K : 0;
+            for (int i = tid; i < nel; i += kThreads) {
+                const int cell = i / K, k = i - cell * K;
+                const int ry = cell / sw, rx = cell - ry * sw;
+                const int y = oy + ry, x = ox + rx;
+                T v = from_f<T>(0.0f);
+                if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(src_lay + ((int64_t)y * W + x) * K + k);
+                sm.stage[(size_t)(ry * kSW + rx) * K + k] = v;
+            }
+        }
+    }
+
+    // ---------------- phase 1b: SSIM windows, runs of kSegW along x ----------------
+    if (has_rgb && (p.terms & VLG_TERM_SSIM)) {
+        if (tid < kSegs * kWH * 3) {
+            const int c = tid / (kSegs * kWH);
+            const int r2 = tid - c * (kSegs * kWH);
+            const int wy = r2 / kSegs, seg = r2 - wy * kSegs;
+            const int wx0 = seg * kSegW;
+            const int nwin = min(kSegW, kWW - wx0);
+            // column sums over the 3 rows of this window row
+            float ca[kSegW + 2], cb[kSegW + 2], caa[kSegW + 2], cbb[kSegW + 2], cab[kSegW + 2];
+#pragma unroll
+            for (int j = 0; j < kSegW + 2; ++j) {
+                if (j < nwin + 2) {
+                    const float2 v0 = sm.ab[c][(wy + 0) * kRW + wx0 + j];
+                    const float2 v1 = sm.ab[c][(wy + 1) * kRW + wx0 + j];
+                    const float2 v2 = sm.ab[c][(wy + 2) * kRW + wx0 + j];
+                    ca[j] = v0.x + v1.x + v2.x;
+                    cb[j] = v0.y + v1.y + v2.y;
+                    caa[j] = fmaf(v2.x, v2.x, fmaf(v1.x, v1.x, v0.x * v0.x));
+                    cbb[j] = fmaf(v2.y, v2.y, fmaf(v1.y, v1.y, v0.y * v0.y));
+                    cab[j] = fmaf(v2.x, v2.y, fmaf(v1.x, v1.y, v0.x * v0.y));
+                } else {
+                    ca[j] = cb[j] = caa[j] = cbb[j] = cab[j] = 0.f;
+                }
+            }
+            const int i = ty0 - kHalo + wy;
+            const bool row_ok = i >= 0 && i + 2 < H;
+#pragma unroll
+            for (int w = 0; w < kSegW; ++w) {
+                if (w < nwin) {
+                    const int wx = wx0 + w;
+                    const int j = tx0 - kHalo + wx;
+                    const bool valid = row_ok && j >= 0 && j + 2 < W;
+                    float4 kk4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) {
+                        const float inv9 = 1.0f / 9.0f, C1 = 1e-4f, C2 = 9e-4f;
+                        const float mx = (ca[w] + ca[w + 1] + ca[w + 2]) * inv9;
+                        const float my = (cb[w] + cb[w + 1] + cb[w + 2]) * inv9;
+                        const float vx = (caa[w] + caa[w + 1] + caa[w + 2]) * inv9 - mx * mx;
+                        const float vy = (cbb[w] + cbb[w + 1] + cbb[w + 2]) * inv9 - my * my;
+                        const float vxy = (cab[w] + cab[w + 1] + cab[w + 2]) * inv9 - mx * my;
+                        const float n1 = 2.f * mx * my + C1, n2 = 2.f * vxy + C2;
+                        const float d1 = mx * mx + my * my + C1, d2 = vx + vy + C2;
+                        const float inv_d1 = __frcp_rn(d1), inv_d2 = __frcp_rn(d2);
+                        const float r = inv_d1 * inv_d2;
+                        const float S = (n1 * n2) * r;
+                        const float v = (1.0f - S) * 0.5f;
+                        if (wy >= kHalo && wx >= kHalo) s_ssim += fminf(1.0f, fmaxf(0.0f, v));
+                        if (p.need_grad && v >= 0.0f && v <= 1.0f) {
+                            // dS/dx_p = A + B x_p + C y_p; loss = (1-S)/2 / M
+                            const float kk = -p.c_ssim * (2.0f / 9.0f);
+                            kk4.y = kk * (-S * inv_d2);
+                            kk4.z = kk * (n1 * r);
+                            kk4.x = kk * (my * (n2 - n1) * r + S * mx * (inv_d2 - inv_d1));
+                        }
+                    }
+                    sm.k[c][wy * kWW + wx] = kk4;
+                }
+            }
+        }
+    }
+    if (WARP && has_lay) cp_async_commit_wait_all();
+    __syncthreads();
 
     // ---------------- phase 2: own pixel ----------------
     const int ty = tid / kTW, tx = tid - ty * kTW;
@@ -150,48 +309,55 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
     const bool inside = y < H && x < W;
     if (inside) {
         const int64_t o = (int64_t)y * W + x;
+        const int q0 = (ty + kHalo) * kRW + tx + kHalo;
         Taps t;
         if (WARP) {
-            t = make_taps(cc, __ldg(coords + o), y, x);
+            // recompute the border mask / scale from the raw coords (cheap) and reuse the staged xy
+            float mx, my;
+            const float2 xy = source_xy(cc, sm.flow[q0], sm.bx[tx + kHalo], sm.by[ty + kHalo], mx, my);
+            t = taps_from_xy(cc, xy, mx, my);
             m_disp = tap_displacement(cc, t, y, x);
+            m_near = m_disp < (float)VLG_NEAR_RADIUS ? m_disp : 0.0f;
         }
         float gix = 0.f, giy = 0.f;
 
         if (has_rgb) {
-            const int q0 = (ty + kHalo) * kRW + tx + kHalo;
             float dr[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float a = sm.a[c][q0], b = sm.b[c][q0];
+                const float2 ab0 = sm.ab[c][q0];
+                const float a = ab0.x, b = ab0.y;
                 const float d = a - b;
                 float g = 0.f;
                 if (p.terms & VLG_TERM_L1) {
                     s_l1 += fabsf(d);
-                    g = p.c_l1 * sgn(d);
+                    g = signed_c(p.c_l1, d, 1.0f);
                 }
                 if (p.terms & VLG_TERM_GD) {
-                // vertical pairs (reference `xloss`, src/loss.py:21-22): (y -> y+1) owned here
-                if (y + 1 < H) {
-                    const float da = sm.a[c][q0 + kRW] - a, db = sm.b[c][q0 + kRW] - b;
-                    const float tt = fabsf(da) - fabsf(db);
-                    s_gd += fabsf(tt);
-                    g -= p.c_gd * sgn(tt) * sgn(da);
-                }
-                if (y >= 1) {
-                    const float da = a - sm.a[c][q0 - kRW], db = b - sm.b[c][q0 - kRW];
-                    g += p.c_gd * sgn(fabsf(da) - fabsf(db)) * sgn(da);
-                }
-                // horizontal pairs (reference `yloss`, src/loss.py:23-24)
-                if (x + 1 < W) {
-                    const float da = sm.a[c][q0 + 1] - a, db = sm.b[c][q0 + 1] - b;
-                    const float tt = fabsf(da) - fabsf(db);
-                    s_gd += fabsf(tt);
-                    g -= p.c_gd * sgn(tt) * sgn(da);
-                }
-                if (x >= 1) {
-                    const float da = a - sm.a[c][q0 - 1], db = b - sm.b[c][q0 - 1];
-                    g += p.c_gd * sgn(fabsf(da) - fabsf(db)) * sgn(da);
-                }
+                    // vertical pairs (reference `xloss`, src/loss.py:21-22): (y -> y+1) owned here
+                    if (y + 1 < H) {
+                        const float2 v = sm.ab[c][q0 + kRW];
+                        const float da = v.x - a, tt = fabsf(da) - fabsf(v.y - b);
+                        s_gd += fabsf(tt);
+                        g -= signed_c(p.c_gd, tt, da);
+                    }
+                    if (y >= 1) {
+                        const float2 v = sm.ab[c][q0 - kRW];
+                        const float da = a - v.x;
+                        g += signed_c(p.c_gd, fabsf(da) - fabsf(b - v.y), da);
+                    }
+                    // horizontal pairs (reference `yloss`, src/loss.py:23-24)
+                    if (x + 1 < W) {
+                        const float2 v = sm.ab[c][q0 + 1];
+                        const float da = v.x - a, tt = fabsf(da) - fabsf(v.y - b);
+                        s_gd += fabsf(tt);
+                        g -= signed_c(p.c_gd, tt, da);
+                    }
+                    if (x >= 1) {
+                        const float2 v = sm.ab[c][q0 - 1];
+                        const float da = a - v.x;
+                        g += signed_c(p.c_gd, fabsf(da) - fabsf(b - v.y), da);
+                    }
                 }
                 if (p.need_grad && (p.terms & VLG_TERM_SSIM)) {
                     // SSIM adjoint: the <=9 windows whose footprint contains this pixel
@@ -200,10 +366,8 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
                     for (int di = 0; di < 3; ++di)
 #pragma unroll
                         for (int dj = 0; dj < 3; ++dj) {
-                            const int w = (ty + di) * kWW + tx + dj;
-                            sA += sm.k[c][0][w];
-                            sB += sm.k[c][1][w];
-                            sC += sm.k[c][2][w];
+                            const float4 kk = sm.k[c][(ty + di) * kWW + tx + dj];
+                            sA += kk.x; sB += kk.y; sC += kk.z;
                         }
                     g += sA + sB * a + sC * b;
                 }
@@ -222,8 +386,30 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
 
         if (has_lay) {
             float z[K];
-            if (WARP) gather_px<T, K>(src_lay, cc, t, z);
-            else load_px<T, K>(src_lay + o * K, z);
+            const T *st00 = nullptr;   // smem address of the nw tap when all four taps are staged
+            if (WARP) {
+                const int rx = t.x0 - ox, ry = t.y0 - oy;
+                if (rx >= 0 && rx + 1 < sw && ry >= 0 && ry + 1 < sh) {
+                    st00 = sm.stage + (size_t)(ry * kSW + rx) * K;
+                    float v[K];
+                    load_px_smem<T, K>(st00, v);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) z[k] = __fmul_rn(v[k], t.nw);
+                    load_px_smem<T, K>(st00 + K, v);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) z[k] = __fmaf_rn(v[k], t.ne, z[k]);
+                    load_px_smem<T, K>(st00 + kSW * K, v);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) z[k] = __fmaf_rn(v[k], t.sw, z[k]);
+                    load_px_smem<T, K>(st00 + kSW * K + K, v);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) z[k] = __fmaf_rn(v[k], t.se, z[k]);
+                } else {
+                    gather_px<T, K>(src_lay, cc, t, z);   // taps outside the staged window: global path
+                }
+            } else {
+                load_px<T, K>(src_lay + o * K, z);
+            }
             float m = z[0];
             int best = 0;
 #pragma unroll
@@ -234,13 +420,14 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
             const bool lab_ok = lab >= 0 && lab < K;
             if (!lab_ok && lab != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
             float e[K], se = 0.f, zl = 0.f;
+            const float ml2 = m * 1.4426950408889634f;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                e[k] = expf(z[k] - m);
+                e[k] = exp2f(fmaf(z[k], 1.4426950408889634f, -ml2));
                 se += e[k];
-                if (k == (int)lab) zl = z[k];
+                zl = fmaf(k == (int)lab ? 1.0f : 0.0f, z[k], zl);   // arithmetic select keeps z[] in registers
             }
-            if (lab_ok) s_ce += (logf(se) + m) - zl;
+            if (lab_ok) s_ce += (__logf(se) + m) - zl;
             if (p.need_grad) {
                 const float nv = (float)p.hdr->n_valid;
                 const float cce = lab_ok ? p.w_ce_over_scale / nv : 0.0f;
@@ -251,7 +438,8 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
                     m_grad = fmaxf(m_grad, fabsf(e[k]));
                 }
                 if (WARP) {
-                    coord_grad_px<T, K>(src_lay, cc, t, e, gix, giy);
+                    if (st00) coord_grad_smem<T, K>(st00, kSW * K, t, e, gix, giy);
+                    else coord_grad_px<T, K>(src_lay, cc, t, e, gix, giy);
                     if (p.d_out_lay) store_px<float, K>(reinterpret_cast<float *>(p.d_out_lay) + (img_px + o) * K, e);
                 } else if (p.d_out_lay) {
                     store_px<T, K>(reinterpret_cast<T *>(p.d_out_lay) + (img_px + o) * K, e);
@@ -262,30 +450,30 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
         if (WARP) {
             float gx = t.mx * gix, gy = t.my * giy;
             if (p.do_tv) {
-                const float2 f = __ldg(coords + o);
+                const float2 f = sm.flow[q0];
                 if (y + 1 < H) {
-                    const float2 f1 = __ldg(coords + o + W);
+                    const float2 f1 = sm.flow[q0 + kRW];
                     const float dx = f1.x - f.x, dy = f1.y - f.y;
                     s_tvh += fabsf(dx) + fabsf(dy);
-                    gx -= p.c_tvh * sgn(dx);
-                    gy -= p.c_tvh * sgn(dy);
+                    gx -= signed_c(p.c_tvh, dx, 1.0f);
+                    gy -= signed_c(p.c_tvh, dy, 1.0f);
                 }
                 if (y >= 1) {
-                    const float2 f1 = __ldg(coords + o - W);
-                    gx += p.c_tvh * sgn(f.x - f1.x);
-                    gy += p.c_tvh * sgn(f.y - f1.y);
+                    const float2 f1 = sm.flow[q0 - kRW];
+                    gx += signed_c(p.c_tvh, f.x - f1.x, 1.0f);
+                    gy += signed_c(p.c_tvh, f.y - f1.y, 1.0f);
                 }
                 if (x + 1 < W) {
-                    const float2 f1 = __ldg(coords + o + 1);
+                    const float2 f1 = sm.flow[q0 + 1];
                     const float dx = f1.x - f.x, dy = f1.y - f.y;
                     s_tvw += fabsf(dx) + fabsf(dy);
-                    gx -= p.c_tvw * sgn(dx);
-                    gy -= p.c_tvw * sgn(dy);
+                    gx -= signed_c(p.c_tvw, dx, 1.0f);
+                    gy -= signed_c(p.c_tvw, dy, 1.0f);
                 }
                 if (x >= 1) {
-                    const float2 f1 = __ldg(coords + o - 1);
-                    gx += p.c_tvw * sgn(f.x - f1.x);
-                    gy += p.c_tvw * sgn(f.y - f1.y);
+                    const float2 f1 = sm.flow[q0 - 1];
+                    gx += signed_c(p.c_tvw, f.x - f1.x, 1.0f);
+                    gy += signed_c(p.c_tvw, f.y - f1.y, 1.0f);
                 }
             }
             if (p.need_grad && p.d_coords)
@@ -295,7 +483,6 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
 
     // ---------------- phase 3: block reduction -> one partial row per CTA ----------------
     float vals[6] = {s_l1, s_gd, s_ssim, s_ce, s_tvh, s_tvw};
-    const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         const float r = warp_sum(vals[i]);
@@ -303,9 +490,11 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
     }
     m_disp = warp_max(m_disp);
     m_grad = warp_max(m_grad);
+    m_near = warp_max(m_near);
     if (lane == 0) {
         sm.redmax[wid][0] = m_disp;
         sm.redmax[wid][1] = m_grad;
+        sm.redmax[wid][2] = m_near;
     }
     __syncthreads();
     if (tid < kPartialSlots) {
@@ -316,12 +505,14 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
         p.partials[(int64_t)bt * kPartialSlots + tid] = r;
     }
     if (tid == 32) {
-        float d = 0.f, g = 0.f;
+        float d = 0.f, g = 0.f, nr = 0.f;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) {
             d = fmaxf(d, sm.redmax[w][0]);
             g = fmaxf(g, sm.redmax[w][1]);
+            nr = fmaxf(nr, sm.redmax[w][2]);
         }
+        if (WARP && p.tile_disp) p.tile_disp[bt] = nr;
         if (d > 0.f) atomicMax(&p.hdr->maxdisp_bits, __float_as_uint(d));
         if (g > 0.f) atomicMax(&p.hdr->maxgrad_bits, __float_as_uint(g));
     }

@@ -9,6 +9,7 @@
 //              fixed-point integer atomics, which are associative and therefore order-free.
 #pragma once
 #include "vlg_device.cuh"
+#include "vlg_pass1.cuh"  // source_xy / taps_from_xy
 
 namespace vlg {
 
@@ -24,14 +25,23 @@ struct Pass2Params {
     void *d_src_rgb;          // type T, nullable
     void *d_src_lay;
     long long *far_acc;       // [P][3+K] fixed point, nullable (VLG_FLAG_NO_FAR_PATH)
+    const float *tile_disp;   // [n_blocks] per-tile max NEAR displacement written by pass 1
     WsHeader *hdr;
     int64_t HW;
 };
 
-__device__ __forceinline__ int near_radius(const WsHeader *hdr, bool &has_far) {
-    const float md = __uint_as_float(hdr->maxdisp_bits);
-    has_far = md >= (float)kRMax;
-    return has_far ? kRMax : (int)floorf(md) + 1;
+// Gather radius of one source tile: output pixels that can reach it lie within kRMax pixels, i.e.
+// inside the 3x3 neighbourhood of tiles (kRMax < kTH); far pixels (disp >= kRMax) are excluded from
+// the per-tile maxima and travel through the fixed-point path instead.
+__device__ __forceinline__ int near_radius(const Pass2Params &p, int n, int tyi, int txi) {
+    float m = 0.f;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = tyi + dy, xx = txi + dx;
+            if (yy >= 0 && yy < p.tiles_y && xx >= 0 && xx < p.tiles_x)
+                m = fmaxf(m, __ldg(p.tile_disp + ((int64_t)n * p.tiles_y + yy) * p.tiles_x + xx));
+        }
+    return min(kRMax, (int)floorf(m) + 1);
 }
 
 // 2^e such that (sum of <= H*W contributions of magnitude <= maxgrad) * 2^e < 2^62
@@ -64,13 +74,17 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     const int ty0 = (trem / p.tiles_x) * kTH, tx0 = (trem % p.tiles_x) * kTW;
     const int64_t img_px = (int64_t)n * H * W;
 
-    bool has_far;
-    const int r = near_radius(p.hdr, has_far);
+    const bool has_far = __uint_as_float(p.hdr->maxdisp_bits) >= (float)kRMax;
+    const int r = near_radius(p, n, trem / p.tiles_x, trem % p.tiles_x);
     const int qw = kTW + 2 * r, qh = kTH + 2 * r, qn = qw * qh;
     const bool want_rgb = p.d_src_rgb != nullptr && p.d_out_rgb != nullptr;
     const bool want_lay = p.d_src_lay != nullptr && p.d_out_lay != nullptr;
 
     // ---- stage coords and d_out of the candidate region ----
+    __shared__ float s_bx[kQW], s_by[kQH];   // base-grid table: one IEEE division per row / column
+    if (tid < qw) s_bx[tid] = base_coord(tx0 - r + tid, cc.Wm1);
+    else if (tid >= 64 && tid < 64 + qh) s_by[tid - 64] = base_coord(ty0 - r + tid - 64, cc.Hm1);
+    __syncthreads();
     const float2 *coords = reinterpret_cast<const float2 *>(p.coords) + img_px;
     const float qnan = __int_as_float(0x7fc00000);
     for (int q = tid; q < qn; q += kThreads) {
@@ -78,9 +92,12 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
         const int y = ty0 - r + ry, x = tx0 - r + rx;
         float2 xy = make_float2(qnan, qnan);
         if (y >= 0 && y < H && x >= 0 && x < W) {
-            const Taps t = make_taps(cc, __ldg(coords + (int64_t)y * W + x), y, x);
-            const bool far = has_far && tap_displacement(cc, t, y, x) >= (float)kRMax;
-            if (!far) xy = make_float2(t.ix, t.iy);
+            float mx, my;
+            const float2 s = source_xy(cc, __ldg(coords + (int64_t)y * W + x), s_bx[rx], s_by[ry], mx, my);
+            const float fx0 = floorf(s.x), fy0 = floorf(s.y);
+            const bool dead = fx0 < -1.0f || fx0 >= (float)W || fy0 < -1.0f || fy0 >= (float)H;  // no tap inside
+            const bool far = !dead && fmaxf(fabsf(s.x - (float)x), fabsf(s.y - (float)y)) >= (float)kRMax;
+            if (!far && !dead) xy = s;
         }
         s_xy[q] = xy;
     }

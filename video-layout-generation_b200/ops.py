@@ -169,12 +169,9 @@ class _WarpLossFn(torch.autograd.Function):
         ctx.grads = (d_a if need_a else None, d_b if need_b else None, d_c if need_c else None)
         ctx.consumed = False
         ctx.workspace = ws  # holds the status word; freed with the graph
-        total = loss[_cabi.LOSS_TOTAL]
-        ctx.mark_non_differentiable(loss)
-        if arg is not None:
-            ctx.mark_non_differentiable(arg)
-            return total, loss, arg
-        return total, loss, None
+        total = loss[_cabi.LOSS_TOTAL].clone()   # own storage: `loss` itself is returned non-differentiable
+        ctx.mark_non_differentiable(*([loss] if arg is None else [loss, arg]))  # one call only
+        return total, loss, arg
 
     @staticmethod
     def backward(ctx, g_total, g_loss, g_arg):
@@ -227,10 +224,8 @@ class _PixelLossFn(torch.autograd.Function):
                                          _ptr(d_z), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
         ctx.grads = (d_a, d_z)
         ctx.consumed = False
-        ctx.mark_non_differentiable(loss)
-        if arg is not None:
-            ctx.mark_non_differentiable(arg)
-        return loss[_cabi.LOSS_TOTAL], loss, arg
+        ctx.mark_non_differentiable(*([loss] if arg is None else [loss, arg]))  # one call only
+        return loss[_cabi.LOSS_TOTAL].clone(), loss, arg
 
     @staticmethod
     def backward(ctx, g_total, g_loss, g_arg):
