@@ -46,6 +46,7 @@ static int check_problem(const vlg_problem_t *p) {
     if (!p) return fail(VLG_ERR_ARG, "problem is NULL");
     if (p->N < 1 || p->H < 2 || p->W < 2) return fail(VLG_ERR_ARG, "need N>=1, H>=2, W>=2 (got %lld,%lld,%lld)", (long long)p->N, (long long)p->H, (long long)p->W);
     if (p->N * p->H * p->W >= (1ll << 31)) return fail(VLG_ERR_UNSUPPORTED, "N*H*W must be < 2^31");
+    if (p->N > 65535 || (p->H + 7) / 8 > 65535) return fail(VLG_ERR_UNSUPPORTED, "N and H/8 must fit a CUDA grid dimension (65535)");
     if (!k_supported(p->K)) return fail(VLG_ERR_UNSUPPORTED, "K=%lld not compiled in (see VLG_FOR_EACH_K)", (long long)p->K);
     if (p->dtype != VLG_F32 && p->dtype != VLG_BF16) return fail(VLG_ERR_ARG, "bad dtype %d", p->dtype);
     if (p->padding != VLG_PAD_ZEROS && p->padding != VLG_PAD_BORDER) return fail(VLG_ERR_ARG, "bad padding %d", p->padding);
@@ -60,14 +61,16 @@ static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
     L.n_blocks = p->N * tiles_x(p->W) * tiles_y(p->H);
     size_t off = 0;
     L.header = off; off = align_up(off + sizeof(WsHeader), 256);
+    L.tile_flags = off; off = align_up(off + (size_t)L.n_blocks * sizeof(uint32_t), 256);   // zeroed together with the header
     L.partials = off; off = align_up(off + (size_t)L.n_blocks * kPartialSlots * sizeof(float), 256);
     L.tile_disp = off; off = align_up(off + (size_t)L.n_blocks * sizeof(float), 256);
-    L.dout_rgb = L.dout_lay = L.far_acc = 0;
+    L.dout_rgb = L.dout_lay = L.far_acc = L.far_list = 0;
     if (with_src_grad) {
         L.dout_rgb = off; off = align_up(off + P * 3 * sizeof(float), 256);
         L.dout_lay = off; off = align_up(off + P * p->K * sizeof(float), 256);
         if (!(p->flags & VLG_FLAG_NO_FAR_PATH)) {
             L.far_acc = off; off = align_up(off + P * (3 + p->K) * sizeof(long long), 256);
+            L.far_list = off; off = align_up(off + P * sizeof(int), 256);
         }
     }
     L.total = off;
@@ -207,8 +210,10 @@ static int launch_pass1(bool warp, const Pass1Params &pp, int64_t n_blocks, cuda
         if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass1): %s", cudaGetErrorString(e));
         attr_done = true;
     }
-    if (warp) pass1_kernel<T, K, true><<<(unsigned)n_blocks, kThreads, smem_warp, st>>>(pp);
-    else pass1_kernel<T, K, false><<<(unsigned)n_blocks, kThreads, smem_plain, st>>>(pp);
+    const dim3 grid((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N);
+    (void)n_blocks;
+    if (warp) pass1_kernel<T, K, true><<<grid, kThreads, smem_warp, st>>>(pp);
+    else pass1_kernel<T, K, false><<<grid, kThreads, smem_plain, st>>>(pp);
     return check_launch("pass1_kernel");
 }
 
@@ -225,14 +230,13 @@ static int dispatch_pass1(const vlg_problem_t *prob, bool warp, const Pass1Param
 
 template <typename T, int K>
 static int launch_pass2(const Pass2Params &pp, int64_t n_blocks, int64_t P, const vlg_problem_t *prob, size_t far_words, cudaStream_t st) {
-    if (pp.far_acc || (prob->flags & VLG_FLAG_NO_FAR_PATH)) {
-        far_zero_kernel<<<148 * 4, 256, 0, st>>>(pp.far_acc, (int64_t)far_words, pp.hdr, prob->flags, pp.hdr);
+    (void)P; (void)far_words; (void)prob;
+    if (pp.far_acc) {   // both exit at once unless pass 1 queued far pixels
+        far_zero_kernel<K><<<148 * 2, kThreads, 0, st>>>(pp);
         int rc = check_launch("far_zero_kernel");
         if (rc) return rc;
-    }
-    if (pp.far_acc) {
-        far_scatter_kernel<K><<<148 * 8, 256, 0, st>>>(pp, P);
-        int rc = check_launch("far_scatter_kernel");
+        far_scatter_kernel<K><<<148 * 2, 256, 0, st>>>(pp);
+        rc = check_launch("far_scatter_kernel");
         if (rc) return rc;
     }
     constexpr size_t smem = pass2_smem_bytes<K>();
@@ -242,7 +246,8 @@ static int launch_pass2(const Pass2Params &pp, int64_t n_blocks, int64_t P, cons
         if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass2): %s", cudaGetErrorString(e));
         attr_done = true;
     }
-    pass2_kernel<T, K><<<(unsigned)n_blocks, kThreads, smem, st>>>(pp);
+    (void)n_blocks;
+    pass2_kernel<T, K><<<dim3((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N), kThreads, smem, st>>>(pp);
     return check_launch("pass2_kernel");
 }
 
@@ -262,7 +267,8 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
                      const WsLayout &L, cudaStream_t st) {
     char *ws = (char *)workspace;
     WsHeader *hdr = (WsHeader *)(ws + L.header);
-    cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(WsHeader), st);
+    // header + per-tile far flags are contiguous: one memset node resets both
+    cudaError_t e = cudaMemsetAsync(hdr, 0, L.partials - L.header, st);
     if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "memset header: %s", cudaGetErrorString(e));
     const int64_t P = prob->N * prob->H * prob->W;
     const bool has_lay = src_layout && tgt_label;
@@ -295,6 +301,8 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.out_argmax = out_argmax;
     pp.partials = (float *)(ws + L.partials);
     pp.tile_disp = (float *)(ws + L.tile_disp);
+    pp.tile_flags = (uint32_t *)(ws + L.tile_flags);
+    pp.far_list = (warp && d_out_lay && L.far_list) ? (int *)(ws + L.far_list) : nullptr;
     pp.hdr = hdr;
     pp.flags = prob->flags;
     return dispatch_pass1(prob, warp, pp, L.n_blocks, st);
@@ -359,6 +367,8 @@ int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src
     pp.d_out_lay = (const float *)(ws + L.dout_lay);
     pp.d_src_rgb = d_src_rgb; pp.d_src_lay = d_src_layout;
     pp.far_acc = L.far_acc ? (long long *)(ws + L.far_acc) : nullptr;
+    pp.far_list = L.far_list ? (const int *)(ws + L.far_list) : nullptr;
+    pp.tile_flags = (const uint32_t *)(ws + L.tile_flags);
     pp.hdr = (WsHeader *)(ws + L.header);
     pp.tile_disp = (const float *)(ws + L.tile_disp);
     pp.HW = prob->H * prob->W;

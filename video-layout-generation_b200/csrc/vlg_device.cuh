@@ -29,7 +29,7 @@ static_assert(sizeof(WsHeader) == 128, "header size");
 constexpr int kPartialSlots = 8;  // l1, gd, ssim, ce, tv_h, tv_w, n_valid(unused), spare
 
 struct WsLayout {
-    size_t header, partials, tile_disp, dout_rgb, dout_lay, far_acc, total;
+    size_t header, tile_flags, partials, tile_disp, dout_rgb, dout_lay, far_acc, far_list, total;
     int64_t n_blocks;
 };
 
@@ -316,6 +316,44 @@ __device__ __forceinline__ void coord_grad_smem(const T *p00, int row_stride, co
     gix += (dne - dnw) * wy0 + (dse - dsw) * wy1;
     giy += (dsw - dnw) * wx0 + (dse - dne) * wx1;
 }
+
+// ---------------------------------------------------------------- Blackwell packed fp32x2 math
+// sm_100 adds FFMA2 / FMUL2 / FADD2 (two IEEE fp32 lanes per instruction, one issue slot): the
+// per-channel loops are issue-bound, so they run on channel PAIRS.  Each lane rounds exactly like
+// the scalar op, so the bit-exact FMA chain of Appendix A.6 is preserved.
+template <int C>
+__device__ __forceinline__ void mul2_bcast(float (&z)[C], const float (&v)[C], float w) {
+    const float2 w2 = make_float2(w, w);
+#pragma unroll
+    for (int j = 0; j + 1 < C; j += 2) {
+        const float2 r = __fmul2_rn(make_float2(v[j], v[j + 1]), w2);
+        z[j] = r.x; z[j + 1] = r.y;
+    }
+    if (C & 1) z[C - 1] = __fmul_rn(v[C - 1], w);
+}
+template <int C>
+__device__ __forceinline__ void fma2_bcast(float (&z)[C], const float (&v)[C], float w) {
+    const float2 w2 = make_float2(w, w);
+#pragma unroll
+    for (int j = 0; j + 1 < C; j += 2) {
+        const float2 r = __ffma2_rn(make_float2(v[j], v[j + 1]), w2, make_float2(z[j], z[j + 1]));
+        z[j] = r.x; z[j + 1] = r.y;
+    }
+    if (C & 1) z[C - 1] = __fmaf_rn(v[C - 1], w, z[C - 1]);
+}
+template <int C>
+__device__ __forceinline__ float dot2(const float (&g)[C], const float (&v)[C]) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j + 1 < C; j += 2) acc = __ffma2_rn(make_float2(g[j], g[j + 1]), make_float2(v[j], v[j + 1]), acc);
+    float r = acc.x + acc.y;
+    if (C & 1) r = fmaf(g[C - 1], v[C - 1], r);
+    return r;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1,5 +1,5 @@
 // vlg_pass1.cuh -- pass 1 of the fused op: warp + every per-pixel loss term + d(loss)/d(warped)
-// + d(loss)/d(coords) in ONE kernel, one CTA per 32x8 output tile.
+// + d(loss)/d(coords) in ONE kernel, one CTA per 32x8 output tile (grid = tiles_x x tiles_y x N).
 //
 // Loss definitions followed (reference gongaa/video-layout-generation):
 //   L1          src/trainer.py:130,248      mean |a-b| over N*3*H*W, sign(0)=0
@@ -10,14 +10,16 @@
 //   TV          (absent upstream)           mean|d_H flow| + mean|d_W flow|, stencils of loss.py:22,24
 //   composition src/trainer.py:248-251      w_l1*L1 + w_gd*GD + w_ssim*SSIM + w_ce*CE (+ w_tv*TV)
 //
-// Phases of one CTA (256 threads, tile 32x8, rgb halo 2):
+// The kernel is issue-bound, not HBM-bound (profiles/): everything below is organised to spend
+// few instructions per pixel.  Phases of one CTA (256 threads, tile 32x8, rgb halo 2):
 //   0a  base-grid coordinates of the tile's rows/columns -> smem (one IEEE division each)
 //   0b  rgb over tile+halo: sampling coordinates, 4-tap gather of src_rgb, target -> smem;
 //       bounding box of the layout taps of the tile's own pixels (integer smem atomics)
-//   1   cp.async the source-layout bounding box into smem (zero-filled outside the image), and
-//       meanwhile evaluate the 3x3 SSIM windows (runs of 5 windows share their column sums)
-//   2   own pixel: L1 / GD / SSIM-adjoint, layout gather from smem, argmax, softmax-CE,
-//       coordinate gradient, TV, stores
+//   1   cp.async the source-layout bounding box into smem row by row (zero-filled outside the
+//       image), and meanwhile evaluate the 3x3 SSIM windows (runs of 5 share their column sums,
+//       packed fp32x2 math on the (x,y) pairs)
+//   2   own pixel: L1 / GD / SSIM-adjoint, layout gather from smem with FFMA2 on channel pairs,
+//       softmax-CE with ex2/lg2.approx, coordinate gradient, TV, stores
 //   3   block reduction -> one row of partial sums, per-tile displacement maxima
 #pragma once
 #include "vlg_device.cuh"
@@ -46,6 +48,8 @@ struct Pass1Params {
     int64_t *out_argmax;    // nullable
     float *partials;        // [n_blocks][kPartialSlots]
     float *tile_disp;       // [n_blocks] max displacement among the tile's NEAR output pixels (WARP)
+    int *far_list;          // [P] compacted indices of FAR output pixels (nullable: no source gradient / no far path)
+    uint32_t *tile_flags;   // [n_blocks] != 0 where a far pixel lands in that SOURCE tile (zeroed with the header)
     WsHeader *hdr;
     uint32_t flags;
 };
@@ -60,7 +64,7 @@ static_assert(kSegs * kWH * 3 <= kThreads, "one SSIM run per thread");
 template <typename T, int K>
 struct Pass1Smem {
     float2 ab[3][kRN];      // (warped-or-given rgb, target rgb) over the tile + halo 2
-    float2 flow[kRN];       // raw coords (TV stencil)
+    float2 flow[kRN];       // raw coords (TV stencil, tap recomputation)
     float4 k[3][kWN];       // per-window SSIM adjoint coefficients (A,B,C,-)
     float bx[kRW], by[kRH]; // base-grid coordinates of the region's columns / rows
     float red[kThreads / 32][kPartialSlots];
@@ -123,6 +127,16 @@ __device__ __forceinline__ float signed_c(float c, float u, float v) {
     const unsigned s = (__float_as_uint(u) ^ __float_as_uint(v)) & 0x80000000u;
     return (u == 0.0f || v == 0.0f) ? 0.0f : __uint_as_float(__float_as_uint(c) | s);
 }
+// +-c with the sign of u, 0 if u is 0
+__device__ __forceinline__ float signed_c1(float c, float u) {
+    return u == 0.0f ? 0.0f : __uint_as_float(__float_as_uint(c) | (__float_as_uint(u) & 0x80000000u));
+}
+
+// one channel of one tap read straight from global memory (zero outside the image)
+template <typename T>
+__device__ __forceinline__ float tap_global(const T *img, int C, int c, int y, int x, int H, int W) {
+    return (y >= 0 && y < H && x >= 0 && x < W) ? to_f<T>(__ldg(img + ((int64_t)y * W + x) * C + c)) : 0.0f;
+}
 
 template <typename T, int K, bool WARP>
 __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
@@ -132,10 +146,9 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
     const int H = cc.H, W = cc.W;
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
-    const int bt = blockIdx.x;
-    const int n = bt / (p.tiles_x * p.tiles_y);
-    const int trem = bt - n * (p.tiles_x * p.tiles_y);
-    const int ty0 = (trem / p.tiles_x) * kTH, tx0 = (trem % p.tiles_x) * kTW;
+    const int n = blockIdx.z;
+    const int bt = (n * p.tiles_y + blockIdx.y) * p.tiles_x + blockIdx.x;
+    const int ty0 = blockIdx.y * kTH, tx0 = blockIdx.x * kTW;
     const int64_t img_px = (int64_t)n * H * W;
 
     const bool has_rgb = p.src_rgb != nullptr && p.tgt_rgb != nullptr;
@@ -159,38 +172,42 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
     // ---------------- phase 0b: coordinates + rgb over the tile + halo ----------------
     {
         int bx0 = 1 << 30, by0 = 1 << 30, bx1 = -(1 << 30), by1 = -(1 << 30);
-        for (int q = tid; q < kRN; q += kThreads) {
-            const int ry = q / kRW, rx = q - ry * kRW;
-            const int y = ty0 - kHalo + ry, x = tx0 - kHalo + rx;
-            float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
-            float2 xy = make_float2(0.f, 0.f), fl = make_float2(0.f, 0.f);
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const int64_t o = (int64_t)y * W + x;
-                if (WARP) {
-                    float mx, my;
-                    fl = __ldg(coords + o);
-                    xy = source_xy(cc, fl, sm.bx[rx], sm.by[ry], mx, my);
-                    if (has_rgb) {
-                        const Taps t = taps_from_xy(cc, xy, mx, my);
-                        gather_px<T, 3>(src_rgb, cc, t, a);
-                    }
-                    const bool own = ry >= kHalo && ry < kHalo + kTH && rx >= kHalo && rx < kHalo + kTW;
-                    if (own && has_lay) {
-                        const int x0 = (int)fminf(fmaxf(floorf(xy.x), -4.0f), (float)W + 4.0f);
-                        const int y0 = (int)fminf(fmaxf(floorf(xy.y), -4.0f), (float)H + 4.0f);
-                        bx0 = min(bx0, x0); bx1 = max(bx1, x0);
-                        by0 = min(by0, y0); by1 = max(by1, y0);
-                    }
-                } else if (has_rgb) {
-                    load_px<T, 3>(src_rgb + o * 3, a);
-                }
-                if (has_rgb) load_px<T, 3>(tgt_rgb + o * 3, b);
-            }
-            if (has_rgb) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) sm.ab[c][q] = make_float2(a[c], b[c]);
+        for (int it = 0; it < (kRN + kThreads - 1) / kThreads; ++it) {
+            const int q = tid + it * kThreads;
+            if (q < kRN) {
+                const int ry = q / kRW, rx = q - ry * kRW;
+                const int y = ty0 - kHalo + ry, x = tx0 - kHalo + rx;
+                float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
+                float2 fl = make_float2(0.f, 0.f);
+                if (y >= 0 && y < H && x >= 0 && x < W) {
+                    const int64_t o = (int64_t)y * W + x;
+                    if (WARP) {
+                        float mx, my;
+                        fl = __ldg(coords + o);
+                        const float2 xy = source_xy(cc, fl, sm.bx[rx], sm.by[ry], mx, my);
+                        if (has_rgb) {
+                            const Taps t = taps_from_xy(cc, xy, mx, my);
+                            gather_px<T, 3>(src_rgb, cc, t, a);
+                        }
+                        const bool own = ry >= kHalo && ry < kHalo + kTH && rx >= kHalo && rx < kHalo + kTW;
+                        if (own && has_lay) {
+                            const int x0 = (int)fminf(fmaxf(floorf(xy.x), -4.0f), (float)W + 4.0f);
+                            const int y0 = (int)fminf(fmaxf(floorf(xy.y), -4.0f), (float)H + 4.0f);
+                            bx0 = min(bx0, x0); bx1 = max(bx1, x0);
+                            by0 = min(by0, y0); by1 = max(by1, y0);
+                        }
+                    } else if (has_rgb) {
+                        load_px<T, 3>(src_rgb + o * 3, a);
+                    }
+                    if (has_rgb) load_px<T, 3>(tgt_rgb + o * 3, b);
+                }
+                if (has_rgb) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sm.ab[c][q] = make_float2(a[c], b[c]);
+                }
+                if (WARP) sm.flow[q] = fl;
             }
-            if (WARP) sm.flow[q] = fl;
         }
         if (WARP && has_lay) {
             bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
@@ -203,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
         __syncthreads();
     }
 
-    // ---------------- phase 1a: stage the source-layout window (async) ----------------
+    // ---------------- phase 1a: stage the source-layout window (async, one warp per row) --------
     // window origin = min tap; extent clipped to the stage capacity.  Cells outside the image are
     // zero-filled, so in-window taps need no bounds predicate (torch skips out-of-image taps).
     int ox = 0, oy = 0, sw = 0, sh = 0;
@@ -211,30 +228,31 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
         ox = sm.bbox[0]; oy = sm.bbox[1];
         sw = min(kSW, sm.bbox[2] + 2 - ox);
         sh = min(kSH, sm.bbox[3] + 2 - oy);
-        constexpr int VB = vec_bytes(K * (int)sizeof(T)) ;
         constexpr int PXB = K * (int)sizeof(T);
-        if constexpr (VB == 16) {
-            constexpr int VPP = PXB / 16;
-            const int nvec = sw > 0 && sh > 0 ? sw * sh * VPP : 0;
-            for (int i = tid; i < nvec; i += kThreads) {
-                const int cell = i / VPP, v = i - cell * VPP;
-                const int ry = cell / sw, rx = cell - ry * sw;
-                const int y = oy + ry, x = ox + rx;
-                char *dst = reinterpret_cast<char *>(sm.stage) + ((size_t)(ry * kSW + rx) * PXB + v * 16);
-                if (y >= 0 && y < H && x >= 0 && x < W)
-                    cp_async16(dst, reinterpret_cast<const char *>(src_lay) + ((int64_t)y * W + x) * PXB + v * 16);
-                else
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
-            }
-        } else {
-            const int nel = sw > 0 && sh > 0 ? sw * sh * K : 0;
-            for (int i = tid; i < nel; i += kThreads) {
-                const int cell = i / K, k = i - cell * K;
-                const int ry = cell / sw, rx = cell - ry * sw;
-                const int y = oy + ry, x = ox + rx;
-                T v = from_f<T>(0.0f);
-                if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(src_lay + ((int64_t)y * W + x) * K + k);
-                sm.stage[(size_t)(ry * kSW + rx) * K + k] = v;
+        constexpr int VB = vec_bytes(PXB);
+        if (sw > 0 && sh > 0) {
+            const int xa = min(max(0, ox), ox + sw), xb = max(min(ox + sw, W), xa);   // in-image columns [xa, xb)
+            for (int ry = wid; ry < sh; ry += kThreads / 32) {
+                const int y = oy + ry;
+                char *drow = reinterpret_cast<char *>(sm.stage) + (size_t)ry * kSW * PXB;
+                T *zrow = reinterpret_cast<T *>(drow);
+                const T zero = from_f<T>(0.0f);
+                if (y < 0 || y >= H) {
+                    for (int i = lane; i < sw * K; i += 32) zrow[i] = zero;
+                    continue;
+                }
+                for (int i = lane; i < (xa - ox) * K; i += 32) zrow[i] = zero;
+                for (int i = lane; i < (ox + sw - xb) * K; i += 32) zrow[(size_t)(xb - ox) * K + i] = zero;
+                const char *srow = reinterpret_cast<const char *>(src_lay) + ((int64_t)y * W + xa) * PXB;
+                char *d = drow + (size_t)(xa - ox) * PXB;
+                const int nbytes = (xb - xa) * PXB;
+                if constexpr (VB == 16) {
+                    for (int i = lane * 16; i < nbytes; i += 32 * 16) cp_async16(d + i, srow + i);
+                } else {
+                    const T *sp = reinterpret_cast<const T *>(srow);
+                    T *dp = reinterpret_cast<T *>(d);
+                    for (int i = lane; i < (xb - xa) * K; i += 32) dp[i] = __ldg(sp + i);
+                }
             }
         }
     }
@@ -247,52 +265,52 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
             const int wy = r2 / kSegs, seg = r2 - wy * kSegs;
             const int wx0 = seg * kSegW;
             const int nwin = min(kSegW, kWW - wx0);
-            // column sums over the 3 rows of this window row
-            float ca[kSegW + 2], cb[kSegW + 2], caa[kSegW + 2], cbb[kSegW + 2], cab[kSegW + 2];
+            // column sums over the 3 rows: (sum x, sum y), (sum x^2, sum y^2), sum xy
+            float2 cs[kSegW + 2], cq[kSegW + 2];
+            float cxy[kSegW + 2];
+            const float2 *row0 = &sm.ab[c][wy * kRW + wx0];
 #pragma unroll
             for (int j = 0; j < kSegW + 2; ++j) {
                 if (j < nwin + 2) {
-                    const float2 v0 = sm.ab[c][(wy + 0) * kRW + wx0 + j];
-                    const float2 v1 = sm.ab[c][(wy + 1) * kRW + wx0 + j];
-                    const float2 v2 = sm.ab[c][(wy + 2) * kRW + wx0 + j];
-                    ca[j] = v0.x + v1.x + v2.x;
-                    cb[j] = v0.y + v1.y + v2.y;
-                    caa[j] = fmaf(v2.x, v2.x, fmaf(v1.x, v1.x, v0.x * v0.x));
-                    cbb[j] = fmaf(v2.y, v2.y, fmaf(v1.y, v1.y, v0.y * v0.y));
-                    cab[j] = fmaf(v2.x, v2.y, fmaf(v1.x, v1.y, v0.x * v0.y));
+                    const float2 v0 = row0[j], v1 = row0[kRW + j], v2 = row0[2 * kRW + j];
+                    cs[j] = __fadd2_rn(__fadd2_rn(v0, v1), v2);
+                    cq[j] = __ffma2_rn(v2, v2, __ffma2_rn(v1, v1, __fmul2_rn(v0, v0)));
+                    cxy[j] = fmaf(v2.x, v2.y, fmaf(v1.x, v1.y, v0.x * v0.y));
                 } else {
-                    ca[j] = cb[j] = caa[j] = cbb[j] = cab[j] = 0.f;
+                    cs[j] = cq[j] = make_float2(0.f, 0.f);
+                    cxy[j] = 0.f;
                 }
             }
             const int i = ty0 - kHalo + wy;
             const bool row_ok = i >= 0 && i + 2 < H;
+            const float inv9 = 1.0f / 9.0f, C1 = 1e-4f, C2 = 9e-4f;
+            const float2 inv9_2 = make_float2(inv9, inv9);
+            const float kk = -p.c_ssim * (2.0f / 9.0f);
 #pragma unroll
             for (int w = 0; w < kSegW; ++w) {
                 if (w < nwin) {
                     const int wx = wx0 + w;
                     const int j = tx0 - kHalo + wx;
-                    const bool valid = row_ok && j >= 0 && j + 2 < W;
                     float4 kk4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) {
-                        const float inv9 = 1.0f / 9.0f, C1 = 1e-4f, C2 = 9e-4f;
-                        const float mx = (ca[w] + ca[w + 1] + ca[w + 2]) * inv9;
-                        const float my = (cb[w] + cb[w + 1] + cb[w + 2]) * inv9;
-                        const float vx = (caa[w] + caa[w + 1] + caa[w + 2]) * inv9 - mx * mx;
-                        const float vy = (cbb[w] + cbb[w + 1] + cbb[w + 2]) * inv9 - my * my;
-                        const float vxy = (cab[w] + cab[w + 1] + cab[w + 2]) * inv9 - mx * my;
-                        const float n1 = 2.f * mx * my + C1, n2 = 2.f * vxy + C2;
-                        const float d1 = mx * mx + my * my + C1, d2 = vx + vy + C2;
-                        const float inv_d1 = __frcp_rn(d1), inv_d2 = __frcp_rn(d2);
+                    if (row_ok && j >= 0 && j + 2 < W) {
+                        const float2 m2 = __fmul2_rn(__fadd2_rn(__fadd2_rn(cs[w], cs[w + 1]), cs[w + 2]), inv9_2);   // (mx, my)
+                        const float2 mm = __fmul2_rn(m2, m2);
+                        const float2 q2 = __fadd2_rn(__fadd2_rn(cq[w], cq[w + 1]), cq[w + 2]);
+                        const float2 var = __ffma2_rn(q2, inv9_2, make_float2(-mm.x, -mm.y));                        // (vx, vy)
+                        const float mxy = m2.x * m2.y;
+                        const float vxy = fmaf(cxy[w] + cxy[w + 1] + cxy[w + 2], inv9, -mxy);
+                        const float n1 = fmaf(2.f, mxy, C1), n2 = fmaf(2.f, vxy, C2);
+                        const float d1 = mm.x + mm.y + C1, d2 = var.x + var.y + C2;
+                        const float inv_d1 = rcp_approx(d1), inv_d2 = rcp_approx(d2);
                         const float r = inv_d1 * inv_d2;
                         const float S = (n1 * n2) * r;
-                        const float v = (1.0f - S) * 0.5f;
-                        if (wy >= kHalo && wx >= kHalo) s_ssim += fminf(1.0f, fmaxf(0.0f, v));
+                        const float v = fmaf(-0.5f, S, 0.5f);
+                        if (wy >= kHalo && wx >= kHalo) s_ssim += __saturatef(v);
                         if (p.need_grad && v >= 0.0f && v <= 1.0f) {
                             // dS/dx_p = A + B x_p + C y_p; loss = (1-S)/2 / M
-                            const float kk = -p.c_ssim * (2.0f / 9.0f);
                             kk4.y = kk * (-S * inv_d2);
                             kk4.z = kk * (n1 * r);
-                            kk4.x = kk * (my * (n2 - n1) * r + S * mx * (inv_d2 - inv_d1));
+                            kk4.x = kk * (m2.y * (n2 - n1) * r + S * m2.x * (inv_d2 - inv_d1));
                         }
                     }
                     sm.k[c][wy * kWW + wx] = kk4;
@@ -312,12 +330,25 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
         const int q0 = (ty + kHalo) * kRW + tx + kHalo;
         Taps t;
         if (WARP) {
-            // recompute the border mask / scale from the raw coords (cheap) and reuse the staged xy
             float mx, my;
             const float2 xy = source_xy(cc, sm.flow[q0], sm.bx[tx + kHalo], sm.by[ty + kHalo], mx, my);
             t = taps_from_xy(cc, xy, mx, my);
             m_disp = tap_displacement(cc, t, y, x);
             m_near = m_disp < (float)VLG_NEAR_RADIUS ? m_disp : 0.0f;
+            if (m_disp >= (float)VLG_NEAR_RADIUS && p.d_out_lay != nullptr) {
+                // far pixel (rare): queue it for the fixed-point scatter and flag the source tiles it hits
+                if (p.far_list) {
+                    p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = (int)(img_px + o);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const int xx = t.x0 + (k4 & 1), yy = t.y0 + (k4 >> 1);
+                        if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                            atomicOr(&p.tile_flags[(n * p.tiles_y + yy / kTH) * p.tiles_x + xx / kTW], 1u);
+                    }
+                } else {
+                    atomicOr(&p.hdr->status, VLG_STATUS_FAR_TAPS);
+                }
+            }
         }
         float gix = 0.f, giy = 0.f;
 
@@ -331,15 +362,15 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
                 float g = 0.f;
                 if (p.terms & VLG_TERM_L1) {
                     s_l1 += fabsf(d);
-                    g = signed_c(p.c_l1, d, 1.0f);
+                    g = signed_c1(p.c_l1, d);
                 }
                 if (p.terms & VLG_TERM_GD) {
                     // vertical pairs (reference `xloss`, src/loss.py:21-22): (y -> y+1) owned here
                     if (y + 1 < H) {
-                        const float2 v = sm.ab[c][q0 + kRW];
-                        const float da = v.x - a, tt = fabsf(da) - fabsf(v.y - b);
+                        const float2 dv = __fadd2_rn(sm.ab[c][q0 + kRW], make_float2(-a, -b));
+                        const float tt = fabsf(dv.x) - fabsf(dv.y);
                         s_gd += fabsf(tt);
-                        g -= signed_c(p.c_gd, tt, da);
+                        g -= signed_c(p.c_gd, tt, dv.x);
                     }
                     if (y >= 1) {
                         const float2 v = sm.ab[c][q0 - kRW];
@@ -348,10 +379,10 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
                     }
                     // horizontal pairs (reference `yloss`, src/loss.py:23-24)
                     if (x + 1 < W) {
-                        const float2 v = sm.ab[c][q0 + 1];
-                        const float da = v.x - a, tt = fabsf(da) - fabsf(v.y - b);
+                        const float2 dv = __fadd2_rn(sm.ab[c][q0 + 1], make_float2(-a, -b));
+                        const float tt = fabsf(dv.x) - fabsf(dv.y);
                         s_gd += fabsf(tt);
-                        g -= signed_c(p.c_gd, tt, da);
+                        g -= signed_c(p.c_gd, tt, dv.x);
                     }
                     if (x >= 1) {
                         const float2 v = sm.ab[c][q0 - 1];
@@ -361,15 +392,18 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
                 }
                 if (p.need_grad && (p.terms & VLG_TERM_SSIM)) {
                     // SSIM adjoint: the <=9 windows whose footprint contains this pixel
-                    float sA = 0.f, sB = 0.f, sC = 0.f;
+                    float2 sAB = make_float2(0.f, 0.f);
+                    float sC = 0.f;
+                    const float4 *kp = &sm.k[c][ty * kWW + tx];
 #pragma unroll
                     for (int di = 0; di < 3; ++di)
 #pragma unroll
                         for (int dj = 0; dj < 3; ++dj) {
-                            const float4 kk = sm.k[c][(ty + di) * kWW + tx + dj];
-                            sA += kk.x; sB += kk.y; sC += kk.z;
+                            const float4 kk = kp[di * kWW + dj];
+                            sAB = __fadd2_rn(sAB, make_float2(kk.x, kk.y));
+                            sC += kk.z;
                         }
-                    g += sA + sB * a + sC * b;
+                    g += fmaf(sC, b, fmaf(sAB.y, a, sAB.x));
                 }
                 dr[c] = g;
                 m_grad = fmaxf(m_grad, fabsf(g));
@@ -385,64 +419,93 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
         }
 
         if (has_lay) {
-            float z[K];
+            const int64_t lab = __ldg(p.label + img_px + o);
+            const bool lab_ok = lab >= 0 && lab < K;
+            if (!lab_ok && lab != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
+            const int il = lab_ok ? (int)lab : 0;
+            float z[K], v[K];
+            float vl[4] = {0.f, 0.f, 0.f, 0.f};   // label channel of the four taps
+            float zl;
             const T *st00 = nullptr;   // smem address of the nw tap when all four taps are staged
             if (WARP) {
                 const int rx = t.x0 - ox, ry = t.y0 - oy;
                 if (rx >= 0 && rx + 1 < sw && ry >= 0 && ry + 1 < sh) {
                     st00 = sm.stage + (size_t)(ry * kSW + rx) * K;
-                    float v[K];
-                    load_px_smem<T, K>(st00, v);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) z[k] = __fmul_rn(v[k], t.nw);
-                    load_px_smem<T, K>(st00 + K, v);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) z[k] = __fmaf_rn(v[k], t.ne, z[k]);
-                    load_px_smem<T, K>(st00 + kSW * K, v);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) z[k] = __fmaf_rn(v[k], t.sw, z[k]);
-                    load_px_smem<T, K>(st00 + kSW * K + K, v);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) z[k] = __fmaf_rn(v[k], t.se, z[k]);
+                    load_px_smem<T, K>(st00, v);                 mul2_bcast<K>(z, v, t.nw);
+                    load_px_smem<T, K>(st00 + K, v);             fma2_bcast<K>(z, v, t.ne);
+                    load_px_smem<T, K>(st00 + kSW * K, v);       fma2_bcast<K>(z, v, t.sw);
+                    load_px_smem<T, K>(st00 + kSW * K + K, v);   fma2_bcast<K>(z, v, t.se);
+                    vl[0] = to_f<T>(st00[il]);            vl[1] = to_f<T>(st00[K + il]);
+                    vl[2] = to_f<T>(st00[kSW * K + il]);  vl[3] = to_f<T>(st00[kSW * K + K + il]);
                 } else {
                     gather_px<T, K>(src_lay, cc, t, z);   // taps outside the staged window: global path
+                    vl[0] = tap_global<T>(src_lay, K, il, t.y0, t.x0, H, W);
+                    vl[1] = tap_global<T>(src_lay, K, il, t.y0, t.x0 + 1, H, W);
+                    vl[2] = tap_global<T>(src_lay, K, il, t.y0 + 1, t.x0, H, W);
+                    vl[3] = tap_global<T>(src_lay, K, il, t.y0 + 1, t.x0 + 1, H, W);
                 }
+                // same FMA chain as z[il], so zl == z[il] bit for bit without indexing registers
+                zl = __fmaf_rn(vl[3], t.se, __fmaf_rn(vl[2], t.sw, __fmaf_rn(vl[1], t.ne, __fmul_rn(vl[0], t.nw))));
             } else {
                 load_px<T, K>(src_lay + o * K, z);
+                zl = to_f<T>(__ldg(src_lay + o * K + il));
             }
             float m = z[0];
-            int best = 0;
 #pragma unroll
-            for (int k = 1; k < K; ++k)
-                if (z[k] > m) { m = z[k]; best = k; }   // first maximal index (src/trainer.py:342)
-            if (p.out_argmax) p.out_argmax[img_px + o] = best;
-            const int64_t lab = __ldg(p.label + img_px + o);
-            const bool lab_ok = lab >= 0 && lab < K;
-            if (!lab_ok && lab != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
-            float e[K], se = 0.f, zl = 0.f;
-            const float ml2 = m * 1.4426950408889634f;
+            for (int k = 1; k < K; ++k) m = fmaxf(m, z[k]);
+            if (p.out_argmax) {
+                int best = K - 1;
+#pragma unroll
+                for (int k = K - 2; k >= 0; --k) best = (z[k] == m) ? k : best;   // first maximal index (src/trainer.py:342)
+                p.out_argmax[img_px + o] = best;
+            }
+            // softmax in base 2: e_k = 2^((z_k - m) * log2(e))
+            const float L2E = 1.4426950408889634f;
+            const float ml2 = m * L2E;
+            float se = 0.f;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                e[k] = exp2f(fmaf(z[k], 1.4426950408889634f, -ml2));
-                se += e[k];
-                zl = fmaf(k == (int)lab ? 1.0f : 0.0f, z[k], zl);   // arithmetic select keeps z[] in registers
+                z[k] = ex2_approx(fmaf(z[k], L2E, -ml2));
+                se += z[k];
             }
-            if (lab_ok) s_ce += (__logf(se) + m) - zl;
+            if (lab_ok) s_ce += fmaf(lg2_approx(se), 0.6931471805599453f, m) - zl;
             if (p.need_grad) {
                 const float nv = (float)p.hdr->n_valid;
                 const float cce = lab_ok ? p.w_ce_over_scale / nv : 0.0f;
                 const float inv = cce / se;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    e[k] = e[k] * inv - (k == (int)lab ? cce : 0.0f);
-                    m_grad = fmaxf(m_grad, fabsf(e[k]));
-                }
+                // d/dz_k = cce * (softmax_k - [k == label]); the one-hot part is applied to the label
+                // channel alone (a scalar fix-up store / a rank-1 term of the coordinate gradient)
+                mul2_bcast<K>(z, z, inv);
+                const float gl = fmaf(ex2_approx(fmaf(zl, L2E, -ml2)), inv, -cce);
+                m_grad = fmaxf(m_grad, cce);   // |softmax - onehot| <= 1: an upper bound is all the far path needs
                 if (WARP) {
-                    if (st00) coord_grad_smem<T, K>(st00, kSW * K, t, e, gix, giy);
-                    else coord_grad_px<T, K>(src_lay, cc, t, e, gix, giy);
-                    if (p.d_out_lay) store_px<float, K>(reinterpret_cast<float *>(p.d_out_lay) + (img_px + o) * K, e);
+                    float dnw, dne, dsw, dse;
+                    if (st00) {
+                        load_px_smem<T, K>(st00, v);                 dnw = dot2<K>(z, v);
+                        load_px_smem<T, K>(st00 + K, v);             dne = dot2<K>(z, v);
+                        load_px_smem<T, K>(st00 + kSW * K, v);       dsw = dot2<K>(z, v);
+                        load_px_smem<T, K>(st00 + kSW * K + K, v);   dse = dot2<K>(z, v);
+                        dnw = fmaf(-cce, vl[0], dnw); dne = fmaf(-cce, vl[1], dne);
+                        dsw = fmaf(-cce, vl[2], dsw); dse = fmaf(-cce, vl[3], dse);
+                        const float wx1 = t.ix - t.fx0, wx0 = (t.fx0 + 1.0f) - t.ix;
+                        const float wy1 = t.iy - t.fy0, wy0 = (t.fy0 + 1.0f) - t.iy;
+                        gix += (dne - dnw) * wy0 + (dse - dsw) * wy1;
+                        giy += (dsw - dnw) * wx0 + (dse - dne) * wx1;
+                    } else {
+                        float gfull[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) gfull[k] = z[k] - (k == il ? cce : 0.0f);
+                        coord_grad_px<T, K>(src_lay, cc, t, gfull, gix, giy);
+                    }
+                    if (p.d_out_lay) {
+                        float *dst = reinterpret_cast<float *>(p.d_out_lay) + (img_px + o) * K;
+                        store_px<float, K>(dst, z);
+                        if (lab_ok) dst[il] = gl;
+                    }
                 } else if (p.d_out_lay) {
-                    store_px<T, K>(reinterpret_cast<T *>(p.d_out_lay) + (img_px + o) * K, e);
+                    T *dst = reinterpret_cast<T *>(p.d_out_lay) + (img_px + o) * K;
+                    store_px<T, K>(dst, z);
+                    if (lab_ok) dst[il] = from_f<T>(gl);
                 }
             }
         }
@@ -452,28 +515,26 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
             if (p.do_tv) {
                 const float2 f = sm.flow[q0];
                 if (y + 1 < H) {
-                    const float2 f1 = sm.flow[q0 + kRW];
-                    const float dx = f1.x - f.x, dy = f1.y - f.y;
-                    s_tvh += fabsf(dx) + fabsf(dy);
-                    gx -= signed_c(p.c_tvh, dx, 1.0f);
-                    gy -= signed_c(p.c_tvh, dy, 1.0f);
+                    const float2 df = __fadd2_rn(sm.flow[q0 + kRW], make_float2(-f.x, -f.y));
+                    s_tvh += fabsf(df.x) + fabsf(df.y);
+                    gx -= signed_c1(p.c_tvh, df.x);
+                    gy -= signed_c1(p.c_tvh, df.y);
                 }
                 if (y >= 1) {
                     const float2 f1 = sm.flow[q0 - kRW];
-                    gx += signed_c(p.c_tvh, f.x - f1.x, 1.0f);
-                    gy += signed_c(p.c_tvh, f.y - f1.y, 1.0f);
+                    gx += signed_c1(p.c_tvh, f.x - f1.x);
+                    gy += signed_c1(p.c_tvh, f.y - f1.y);
                 }
                 if (x + 1 < W) {
-                    const float2 f1 = sm.flow[q0 + 1];
-                    const float dx = f1.x - f.x, dy = f1.y - f.y;
-                    s_tvw += fabsf(dx) + fabsf(dy);
-                    gx -= signed_c(p.c_tvw, dx, 1.0f);
-                    gy -= signed_c(p.c_tvw, dy, 1.0f);
+                    const float2 df = __fadd2_rn(sm.flow[q0 + 1], make_float2(-f.x, -f.y));
+                    s_tvw += fabsf(df.x) + fabsf(df.y);
+                    gx -= signed_c1(p.c_tvw, df.x);
+                    gy -= signed_c1(p.c_tvw, df.y);
                 }
                 if (x >= 1) {
                     const float2 f1 = sm.flow[q0 - 1];
-                    gx += signed_c(p.c_tvw, f.x - f1.x, 1.0f);
-                    gy += signed_c(p.c_tvw, f.y - f1.y, 1.0f);
+                    gx += signed_c1(p.c_tvw, f.x - f1.x);
+                    gy += signed_c1(p.c_tvw, f.y - f1.y);
                 }
             }
             if (p.need_grad && p.d_coords)

@@ -5,11 +5,14 @@
 // row-major order, the d_out of the output pixels whose bilinear footprint covers it:
 //   near path: output pixels displaced by < VLG_NEAR_RADIUS px are found by scanning the
 //              (2r+1)^2 window around the source pixel in shared memory -- no atomics at all;
-//   far path : the (rare) output pixels displaced further are accumulated with 64-bit
-//              fixed-point integer atomics, which are associative and therefore order-free.
+//              r is chosen per tile from the displacement maxima pass 1 recorded;
+//   far path : the (rare) output pixels displaced further were queued by pass 1; they are
+//              accumulated with 64-bit fixed-point integer atomics (associative, hence
+//              order-free) into the source tiles pass 1 flagged, and only those tiles are
+//              zeroed and read back.
 #pragma once
 #include "vlg_device.cuh"
-#include "vlg_pass1.cuh"  // source_xy / taps_from_xy
+#include "vlg_pass1.cuh"  // source_xy, cp_async16
 
 namespace vlg {
 
@@ -25,6 +28,8 @@ struct Pass2Params {
     void *d_src_rgb;          // type T, nullable
     void *d_src_lay;
     long long *far_acc;       // [P][3+K] fixed point, nullable (VLG_FLAG_NO_FAR_PATH)
+    const int *far_list;      // [far_count] far output pixels queued by pass 1
+    const uint32_t *tile_flags;  // [n_blocks] source tiles that receive far contributions
     const float *tile_disp;   // [n_blocks] per-tile max NEAR displacement written by pass 1
     WsHeader *hdr;
     int64_t HW;
@@ -61,71 +66,68 @@ constexpr size_t pass2_smem_bytes() {
 template <typename T, int K>
 __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *s_xy = reinterpret_cast<float2 *>(smem_raw);               // [kQN] source coords (NaN = skip)
-    float *s_lay = reinterpret_cast<float *>(s_xy + kQN);             // [kQN][K]
-    float *s_rgb = s_lay + (size_t)kQN * K;                            // [kQN][3]
+    float *s_lay = reinterpret_cast<float *>(smem_raw);                 // [kQN][K]   (16-byte aligned rows)
+    float2 *s_xy = reinterpret_cast<float2 *>(s_lay + (size_t)kQN * K); // [kQN] source coords (NaN = skip)
+    float *s_rgb = reinterpret_cast<float *>(s_xy + kQN);              // [kQN][3]
+    __shared__ float s_bx[kQW], s_by[kQH];   // base-grid table: one IEEE division per row / column
 
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
     const int tid = threadIdx.x;
-    const int bt = blockIdx.x;
-    const int n = bt / (p.tiles_x * p.tiles_y);
-    const int trem = bt - n * (p.tiles_x * p.tiles_y);
-    const int ty0 = (trem / p.tiles_x) * kTH, tx0 = (trem % p.tiles_x) * kTW;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int n = blockIdx.z;
+    const int bt = (n * p.tiles_y + blockIdx.y) * p.tiles_x + blockIdx.x;
+    const int ty0 = blockIdx.y * kTH, tx0 = blockIdx.x * kTW;
     const int64_t img_px = (int64_t)n * H * W;
 
-    const bool has_far = __uint_as_float(p.hdr->maxdisp_bits) >= (float)kRMax;
-    const int r = near_radius(p, n, trem / p.tiles_x, trem % p.tiles_x);
-    const int qw = kTW + 2 * r, qh = kTH + 2 * r, qn = qw * qh;
+    const int r = near_radius(p, n, blockIdx.y, blockIdx.x);
+    const int qw = kTW + 2 * r, qh = kTH + 2 * r;
     const bool want_rgb = p.d_src_rgb != nullptr && p.d_out_rgb != nullptr;
     const bool want_lay = p.d_src_lay != nullptr && p.d_out_lay != nullptr;
+    const int xa = max(tx0 - r, 0), xb = min(tx0 - r + qw, W);   // in-image columns of the candidate region
 
-    // ---- stage coords and d_out of the candidate region ----
-    __shared__ float s_bx[kQW], s_by[kQH];   // base-grid table: one IEEE division per row / column
+    // ---- stage d_out of the candidate region: one warp per row, contiguous cp.async ----
+    for (int ry = wid; ry < qh; ry += kThreads / 32) {
+        const int y = ty0 - r + ry;
+        if (y < 0 || y >= H || xb <= xa) continue;
+        const int64_t g0 = img_px + (int64_t)y * W + xa;
+        const int q0 = ry * qw + (xa - (tx0 - r));
+        if (want_lay) {
+            const char *src = reinterpret_cast<const char *>(p.d_out_lay + g0 * K);
+            char *dst = reinterpret_cast<char *>(s_lay + (size_t)q0 * K);
+            const int nbytes = (xb - xa) * K * 4;
+            if constexpr (K % 4 == 0) {
+                for (int i = lane * 16; i < nbytes; i += 32 * 16) cp_async16(dst + i, src + i);
+            } else {
+                for (int i = lane; i < (xb - xa) * K; i += 32) s_lay[(size_t)q0 * K + i] = __ldg(p.d_out_lay + g0 * K + i);
+            }
+        }
+        if (want_rgb)
+            for (int i = lane; i < (xb - xa) * 3; i += 32) s_rgb[q0 * 3 + i] = __ldg(p.d_out_rgb + g0 * 3 + i);
+    }
+    // ---- sampling coordinates of the candidate output pixels ----
     if (tid < qw) s_bx[tid] = base_coord(tx0 - r + tid, cc.Wm1);
     else if (tid >= 64 && tid < 64 + qh) s_by[tid - 64] = base_coord(ty0 - r + tid - 64, cc.Hm1);
     __syncthreads();
     const float2 *coords = reinterpret_cast<const float2 *>(p.coords) + img_px;
     const float qnan = __int_as_float(0x7fc00000);
-    for (int q = tid; q < qn; q += kThreads) {
-        const int ry = q / qw, rx = q - ry * qw;
-        const int y = ty0 - r + ry, x = tx0 - r + rx;
-        float2 xy = make_float2(qnan, qnan);
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            float mx, my;
-            const float2 s = source_xy(cc, __ldg(coords + (int64_t)y * W + x), s_bx[rx], s_by[ry], mx, my);
-            const float fx0 = floorf(s.x), fy0 = floorf(s.y);
-            const bool dead = fx0 < -1.0f || fx0 >= (float)W || fy0 < -1.0f || fy0 >= (float)H;  // no tap inside
-            const bool far = !dead && fmaxf(fabsf(s.x - (float)x), fabsf(s.y - (float)y)) >= (float)kRMax;
-            if (!far && !dead) xy = s;
-        }
-        s_xy[q] = xy;
-    }
-    if (want_lay) {
-        constexpr int V = K % 4 == 0 ? 4 : 1;  // floats per staged vector
-        constexpr int VPP = K / V;             // vectors per pixel
-        for (int i = tid; i < qn * VPP; i += kThreads) {
-            const int q = i / VPP, v = i - q * VPP;
-            const int ry = q / qw, rx = q - ry * qw;
-            const int y = ty0 - r + ry, x = tx0 - r + rx;
+    for (int ry = wid; ry < qh; ry += kThreads / 32) {
+        const int y = ty0 - r + ry;
+        for (int rx = lane; rx < qw; rx += 32) {
+            const int x = tx0 - r + rx;
+            float2 xy = make_float2(qnan, qnan);
             if (y >= 0 && y < H && x >= 0 && x < W) {
-                const float *g = p.d_out_lay + (img_px + (int64_t)y * W + x) * K + v * V;
-                if constexpr (V == 4)
-                    *reinterpret_cast<float4 *>(s_lay + (size_t)q * K + v * 4) = __ldg(reinterpret_cast<const float4 *>(g));
-                else
-                    s_lay[(size_t)q * K + v] = __ldg(g);
+                float mx, my;
+                const float2 s = source_xy(cc, __ldg(coords + (int64_t)y * W + x), s_bx[rx], s_by[ry], mx, my);
+                const float fx0 = floorf(s.x), fy0 = floorf(s.y);
+                const bool dead = fx0 < -1.0f || fx0 >= (float)W || fy0 < -1.0f || fy0 >= (float)H;  // no tap inside
+                const bool far = fmaxf(fabsf(s.x - (float)x), fabsf(s.y - (float)y)) >= (float)kRMax;
+                if (!far && !dead) xy = s;
             }
+            s_xy[ry * qw + rx] = xy;
         }
     }
-    if (want_rgb) {
-        for (int i = tid; i < qn * 3; i += kThreads) {
-            const int q = i / 3, c = i - q * 3;
-            const int ry = q / qw, rx = q - ry * qw;
-            const int y = ty0 - r + ry, x = tx0 - r + rx;
-            if (y >= 0 && y < H && x >= 0 && x < W)
-                s_rgb[q * 3 + c] = __ldg(p.d_out_rgb + (img_px + (int64_t)y * W + x) * 3 + c);
-        }
-    }
+    cp_async_commit_wait_all();
     __syncthreads();
 
     // ---- one thread per source pixel: fixed-order gather ----
@@ -149,20 +151,9 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
             const float wy = ay == 0.0f ? __fsub_rn(__fadd_rn(fy0, 1.0f), xy.y) : __fsub_rn(xy.y, fy0);
             const float w = __fmul_rn(wx, wy);
             if (want_lay) {
-                const float *d = s_lay + (size_t)q * K;
-                if constexpr (K % 4 == 0) {
-#pragma unroll
-                    for (int v = 0; v < K / 4; ++v) {
-                        const float4 dv = *reinterpret_cast<const float4 *>(d + 4 * v);
-                        acc_l[4 * v + 0] = fmaf(w, dv.x, acc_l[4 * v + 0]);
-                        acc_l[4 * v + 1] = fmaf(w, dv.y, acc_l[4 * v + 1]);
-                        acc_l[4 * v + 2] = fmaf(w, dv.z, acc_l[4 * v + 2]);
-                        acc_l[4 * v + 3] = fmaf(w, dv.w, acc_l[4 * v + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) acc_l[k] = fmaf(w, d[k], acc_l[k]);
-                }
+                float v[K];
+                load_px_smem<float, K>(s_lay + (size_t)q * K, v);
+                fma2_bcast<K>(acc_l, v, w);
             }
             if (want_rgb) {
 #pragma unroll
@@ -171,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
         }
     }
     const int64_t so = img_px + (int64_t)sy * W + sx;
-    if (has_far && p.far_acc) {
+    if (p.far_acc && p.tile_flags[bt]) {
         const double inv = 1.0 / far_scale(p.hdr, p.HW);
         const long long *fa = p.far_acc + so * (3 + K);
 #pragma unroll
@@ -183,40 +174,38 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     if (want_lay) store_px<T, K>(reinterpret_cast<T *>(p.d_src_lay) + so * K, acc_l);
 }
 
-// ---- far path: zero the fixed-point accumulators (only when far pixels exist) ----
-__global__ void far_zero_kernel(long long *acc, int64_t n_words, const WsHeader *hdr, uint32_t flags,
-                                WsHeader *hdr_rw) {
-    const float md = __uint_as_float(hdr->maxdisp_bits);
-    if (md < (float)kRMax) return;
-    if (flags & VLG_FLAG_NO_FAR_PATH) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&hdr_rw->status, VLG_STATUS_FAR_TAPS);
-        return;
+// ---- far path: zero the fixed-point accumulators of the flagged source tiles only ----
+template <int K>
+__global__ void __launch_bounds__(kThreads) far_zero_kernel(const Pass2Params p) {
+    if (p.hdr->far_count == 0) return;
+    const int n_tiles = p.N * p.tiles_y * p.tiles_x;
+    const int ty = threadIdx.x / kTW, tx = threadIdx.x - ty * kTW;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (!p.tile_flags[t]) continue;
+        const int n = t / (p.tiles_y * p.tiles_x), rem = t - n * (p.tiles_y * p.tiles_x);
+        const int y = (rem / p.tiles_x) * kTH + ty, x = (rem % p.tiles_x) * kTW + tx;
+        if (y >= p.cc.H || x >= p.cc.W) continue;
+        long long *a = p.far_acc + ((int64_t)n * p.HW + (int64_t)y * p.cc.W + x) * (3 + K);
+#pragma unroll
+        for (int c = 0; c < 3 + K; ++c) a[c] = 0;
     }
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    longlong2 *a2 = reinterpret_cast<longlong2 *>(acc);
-    const int64_t n2 = n_words / 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
-        a2[i] = make_longlong2(0, 0);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && (n_words & 1)) acc[n_words - 1] = 0;
 }
 
-// ---- far path: fixed-point scatter of the far output pixels ----
+// ---- far path: fixed-point scatter of the queued far output pixels ----
 template <int K>
-__global__ void far_scatter_kernel(const Pass2Params p, int64_t P) {
-    const float md = __uint_as_float(p.hdr->maxdisp_bits);
-    if (md < (float)kRMax || p.far_acc == nullptr) return;
+__global__ void far_scatter_kernel(const Pass2Params p) {
+    const unsigned n_far = p.hdr->far_count;
+    if (n_far == 0) return;
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
     const double scale = far_scale(p.hdr, p.HW);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float2 *coords = reinterpret_cast<const float2 *>(p.coords);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n_far; j += gridDim.x * blockDim.x) {
+        const int64_t i = p.far_list[j];
         const int64_t n = i / p.HW;
         const int64_t rem = i - n * p.HW;
         const int y = (int)(rem / W), x = (int)(rem - (int64_t)y * W);
         const Taps t = make_taps(cc, __ldg(coords + i), y, x);
-        if (!(tap_displacement(cc, t, y, x) >= (float)kRMax)) continue;
-        atomicAdd(&p.hdr->far_count, 1u);
         const int xs[4] = {t.x0, t.x0 + 1, t.x0, t.x0 + 1};
         const int ys[4] = {t.y0, t.y0, t.y0 + 1, t.y0 + 1};
         const float ws[4] = {t.nw, t.ne, t.sw, t.se};
