@@ -208,15 +208,23 @@ def main():
     ptr = vops._ptr
 
     def step(i, evs=None):
+        """One pass of the hot path.  The timed region uses the fused entry point (the last pass-1
+        CTA reduces the loss vector); with `evs` the same work is issued piecewise so that CUDA
+        events can bracket each kernel."""
         s = sets[i & 1]
-        vops.check(lib.vlg_warp_loss_bwd_out(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
-                                             ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(d_c), None, int(with_src),
-                                             ptr(ws), ws.numel(), sp))
-        if evs: evs[1].record(stream)
-        vops.check(lib.vlg_reduce_partials(C.byref(prob), ptr(loss), ptr(ws), ws.numel(), sp))
-        if evs: evs[2].record(stream)
-        if with_src:
-            vops.check(lib.vlg_warp_bwd_src(C.byref(prob), ptr(s["flow"]), ptr(d_a), ptr(d_b), ptr(ws), ws.numel(), sp))
+        if evs is None:
+            vops.check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
+                                                 ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(loss), ptr(d_c), ptr(d_a),
+                                                 ptr(d_b), None, ptr(ws), ws.numel(), sp))
+        else:
+            vops.check(lib.vlg_warp_loss_bwd_out(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
+                                                 ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(d_c), None, int(with_src),
+                                                 ptr(ws), ws.numel(), sp))
+            evs[1].record(stream)
+            vops.check(lib.vlg_reduce_partials(C.byref(prob), ptr(loss), ptr(ws), ws.numel(), sp))
+            evs[2].record(stream)
+            if with_src:
+                vops.check(lib.vlg_warp_bwd_src(C.byref(prob), ptr(s["flow"]), ptr(d_a), ptr(d_b), ptr(ws), ws.numel(), sp))
         if dist is not None:
             dist.all_reduce(loss)          # the path's only exchange: one 8-float loss vector
         if evs: evs[3].record(stream)

@@ -64,6 +64,7 @@ static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
     L.tile_flags = off; off = align_up(off + (size_t)L.n_blocks * sizeof(uint32_t), 256);   // zeroed together with the header
     L.partials = off; off = align_up(off + (size_t)L.n_blocks * kPartialSlots * sizeof(float), 256);
     L.tile_disp = off; off = align_up(off + (size_t)L.n_blocks * sizeof(float), 256);
+    L.flagged = off; off = align_up(off + (size_t)L.n_blocks * sizeof(int), 256);
     L.dout_rgb = L.dout_lay = L.far_acc = L.far_list = 0;
     if (with_src_grad) {
         L.dout_rgb = off; off = align_up(off + P * 3 * sizeof(float), 256);
@@ -105,52 +106,26 @@ __global__ void count_valid_kernel(const int64_t *__restrict__ label, int64_t P,
     }
 }
 
-struct ReduceParams {
-    const float *partials;
-    int64_t n_blocks;
-    const WsHeader *hdr;
-    double inv_numel_rgb;   // 1/(Ng*3*H*W)
-    double inv_ssim;        // 1/(Ng*(H-2)*(W-2))
-    double inv_tvh, inv_tvw;
-    double ce_scale;        // N_local/N_global
-    float w_l1, w_gd, w_ssim, w_ce, w_tv;
-    float *out;
-};
-
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
-    __shared__ double s[6][256];
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int64_t b = threadIdx.x; b < p.n_blocks; b += 256) {
-        const float4 lo = __ldg(reinterpret_cast<const float4 *>(p.partials + b * kPartialSlots));
-        const float2 hi = __ldg(reinterpret_cast<const float2 *>(p.partials + b * kPartialSlots + 4));
-        acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w; acc[4] += hi.x; acc[5] += hi.y;
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) s[i][threadIdx.x] = acc[i];
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-#pragma unroll
-            for (int i = 0; i < 6; ++i) s[i][threadIdx.x] += s[i][threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const double nv = (double)p.hdr->n_valid;
-        const double l1 = s[0][0] * p.inv_numel_rgb, gd = s[1][0] * p.inv_numel_rgb;
-        const double ssim = s[2][0] * p.inv_ssim;
-        const double ce = nv > 0 ? s[3][0] / nv * p.ce_scale : 0.0;
-        const double tv = s[4][0] * p.inv_tvh + s[5][0] * p.inv_tvw;
-        p.out[VLG_LOSS_L1] = (float)l1;
-        p.out[VLG_LOSS_GD] = (float)gd;
-        p.out[VLG_LOSS_SSIM] = (float)ssim;
-        p.out[VLG_LOSS_CE] = (float)ce;
-        p.out[VLG_LOSS_TV] = (float)tv;
-        const double tot = (double)p.w_l1 * l1 + (double)p.w_gd * gd + (double)p.w_ssim * ssim +
-                           (double)p.w_ce * ce + (double)p.w_tv * tv;
-        p.out[VLG_LOSS_TOTAL] = (float)tot;
-        p.out[VLG_LOSS_NVALID] = (float)nv;
-        p.out[VLG_LOSS_MAXDISP] = __uint_as_float(p.hdr->maxdisp_bits);
-    }
+    __shared__ double s[6 * 256];
+    reduce_partials_block(p, s);
+}
+
+static ReduceParams make_reduce_params(const vlg_problem_t *prob, const WsLayout &L, char *ws, float *loss_out) {
+    const double Ng = (double)(prob->global_N ? prob->global_N : prob->N);
+    const double H = (double)prob->H, W = (double)prob->W;
+    ReduceParams rp{};
+    rp.partials = (const float *)(ws + L.partials);
+    rp.n_blocks = L.n_blocks;
+    rp.hdr = (const WsHeader *)(ws + L.header);
+    rp.inv_numel_rgb = 1.0 / (Ng * 3 * H * W);
+    rp.inv_ssim = (prob->H > 2 && prob->W > 2) ? 1.0 / (Ng * (H - 2) * (W - 2)) : 0.0;
+    rp.inv_tvh = 1.0 / (Ng * (H - 1) * W * 2);
+    rp.inv_tvw = 1.0 / (Ng * H * (W - 1) * 2);
+    rp.ce_scale = (double)prob->N / Ng;
+    rp.w_l1 = prob->w_l1; rp.w_gd = prob->w_gd; rp.w_ssim = prob->w_ssim; rp.w_ce = prob->w_ce; rp.w_tv = prob->w_tv;
+    rp.out = loss_out;   // NULL: pass 1 does not fuse the final reduction
+    return rp;
 }
 
 template <typename T>
@@ -263,8 +238,8 @@ static int launch_fwd(const vlg_problem_t *prob, const void *src_rgb, const void
 
 static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, const void *src_layout,
                      const float *coords, const void *tgt_rgb, const int64_t *tgt_label, float *d_coords,
-                     void *d_out_rgb, void *d_out_lay, bool need_grad, int64_t *out_argmax, void *workspace,
-                     const WsLayout &L, cudaStream_t st) {
+                     void *d_out_rgb, void *d_out_lay, bool need_grad, int64_t *out_argmax, float *fused_loss_out,
+                     void *workspace, const WsLayout &L, cudaStream_t st) {
     char *ws = (char *)workspace;
     WsHeader *hdr = (WsHeader *)(ws + L.header);
     // header + per-tile far flags are contiguous: one memset node resets both
@@ -303,6 +278,8 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.tile_disp = (float *)(ws + L.tile_disp);
     pp.tile_flags = (uint32_t *)(ws + L.tile_flags);
     pp.far_list = (warp && d_out_lay && L.far_list) ? (int *)(ws + L.far_list) : nullptr;
+    pp.flagged_list = (int *)(ws + L.flagged);
+    pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
     pp.hdr = hdr;
     pp.flags = prob->flags;
     return dispatch_pass1(prob, warp, pp, L.n_blocks, st);
@@ -336,9 +313,10 @@ int vlg_warp_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src
     return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
 }
 
-int vlg_warp_loss_bwd_out(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
-                          const void *tgt_rgb, const int64_t *tgt_label, float *d_coords, int64_t *out_argmax,
-                          int with_src_grad, void *workspace, size_t workspace_bytes, void *stream) {
+static int warp_loss_pass1(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
+                           const void *tgt_rgb, const int64_t *tgt_label, float *d_coords, int64_t *out_argmax,
+                           int with_src_grad, float *fused_loss_out, void *workspace, size_t workspace_bytes,
+                           void *stream) {
     int rc = check_problem(prob);
     if (rc) return rc;
     if (!coords) return fail(VLG_ERR_ARG, "coords is NULL");
@@ -348,7 +326,14 @@ int vlg_warp_loss_bwd_out(const vlg_problem_t *prob, const void *src_rgb, const 
     char *ws = (char *)workspace;
     return run_pass1(prob, true, src_rgb, src_layout, coords, tgt_rgb, tgt_label, d_coords,
                      with_src_grad ? ws + L.dout_rgb : nullptr, with_src_grad ? ws + L.dout_lay : nullptr,
-                     d_coords != nullptr, out_argmax, workspace, L, (cudaStream_t)stream);
+                     d_coords != nullptr, out_argmax, fused_loss_out, workspace, L, (cudaStream_t)stream);
+}
+
+int vlg_warp_loss_bwd_out(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
+                          const void *tgt_rgb, const int64_t *tgt_label, float *d_coords, int64_t *out_argmax,
+                          int with_src_grad, void *workspace, size_t workspace_bytes, void *stream) {
+    return warp_loss_pass1(prob, src_rgb, src_layout, coords, tgt_rgb, tgt_label, d_coords, out_argmax, with_src_grad,
+                           nullptr, workspace, workspace_bytes, stream);
 }
 
 int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src_rgb, void *d_src_layout,
@@ -369,6 +354,7 @@ int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src
     pp.far_acc = L.far_acc ? (long long *)(ws + L.far_acc) : nullptr;
     pp.far_list = L.far_list ? (const int *)(ws + L.far_list) : nullptr;
     pp.tile_flags = (const uint32_t *)(ws + L.tile_flags);
+    pp.flagged_list = (const int *)(ws + L.flagged);
     pp.hdr = (WsHeader *)(ws + L.header);
     pp.tile_disp = (const float *)(ws + L.tile_disp);
     pp.HW = prob->H * prob->W;
@@ -391,19 +377,7 @@ int vlg_reduce_partials(const vlg_problem_t *prob, float *loss_out, void *worksp
     const WsLayout L = ws_layout(prob, 0);
     if (!workspace || workspace_bytes < L.total) return fail(VLG_ERR_WORKSPACE, "workspace too small");
     char *ws = (char *)workspace;
-    const double Ng = (double)(prob->global_N ? prob->global_N : prob->N);
-    const double H = (double)prob->H, W = (double)prob->W;
-    ReduceParams rp{};
-    rp.partials = (const float *)(ws + L.partials);
-    rp.n_blocks = L.n_blocks;
-    rp.hdr = (const WsHeader *)(ws + L.header);
-    rp.inv_numel_rgb = 1.0 / (Ng * 3 * H * W);
-    rp.inv_ssim = (prob->H > 2 && prob->W > 2) ? 1.0 / (Ng * (H - 2) * (W - 2)) : 0.0;
-    rp.inv_tvh = 1.0 / (Ng * (H - 1) * W * 2);
-    rp.inv_tvw = 1.0 / (Ng * H * (W - 1) * 2);
-    rp.ce_scale = (double)prob->N / Ng;
-    rp.w_l1 = prob->w_l1; rp.w_gd = prob->w_gd; rp.w_ssim = prob->w_ssim; rp.w_ce = prob->w_ce; rp.w_tv = prob->w_tv;
-    rp.out = loss_out;
+    const ReduceParams rp = make_reduce_params(prob, L, ws, loss_out);
     reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rp);
     return check_launch("reduce_partials_kernel");
 }
@@ -413,13 +387,10 @@ int vlg_warp_loss_fwd_bwd(const vlg_problem_t *prob, const void *src_rgb, const 
                           void *d_src_rgb, void *d_src_layout, int64_t *out_argmax, void *workspace,
                           size_t workspace_bytes, void *stream) {
     const int with_src = (d_src_rgb || d_src_layout) ? 1 : 0;
-    int rc = vlg_warp_loss_bwd_out(prob, src_rgb, src_layout, coords, tgt_rgb, tgt_label, d_coords, out_argmax,
-                                   with_src, workspace, workspace_bytes, stream);
+    // the last pass-1 CTA performs the final reduction into loss_out: no separate reduce launch
+    int rc = warp_loss_pass1(prob, src_rgb, src_layout, coords, tgt_rgb, tgt_label, d_coords, out_argmax, with_src,
+                             loss_out, workspace, workspace_bytes, stream);
     if (rc) return rc;
-    if (loss_out) {
-        rc = vlg_reduce_partials(prob, loss_out, workspace, workspace_bytes, stream);
-        if (rc) return rc;
-    }
     if (with_src) rc = vlg_warp_bwd_src(prob, coords, d_src_rgb, d_src_layout, workspace, workspace_bytes, stream);
     return rc;
 }
@@ -434,9 +405,7 @@ int vlg_pixel_loss_fwd_bwd(const vlg_problem_t *prob, const void *out_rgb, const
     if ((out_rgb == nullptr) != (tgt_rgb == nullptr)) return fail(VLG_ERR_ARG, "out_rgb and tgt_rgb go together");
     if ((logits == nullptr) != (tgt_label == nullptr)) return fail(VLG_ERR_ARG, "logits and tgt_label go together");
     rc = run_pass1(prob, false, out_rgb, logits, nullptr, tgt_rgb, tgt_label, nullptr, d_out_rgb, d_logits,
-                   d_out_rgb != nullptr || d_logits != nullptr, out_argmax, workspace, L, (cudaStream_t)stream);
-    if (rc) return rc;
-    if (loss_out) rc = vlg_reduce_partials(prob, loss_out, workspace, workspace_bytes, stream);
+                   d_out_rgb != nullptr || d_logits != nullptr, out_argmax, loss_out, workspace, L, (cudaStream_t)stream);
     return rc;
 }
 

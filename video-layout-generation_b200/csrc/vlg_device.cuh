@@ -22,14 +22,66 @@ struct WsHeader {
     uint32_t maxgrad_bits;  // float bits of max |d_out| (scale of the fixed-point far path)
     uint32_t far_count;     // number of far output pixels
     unsigned long long n_valid;  // labels != ignore_index
-    uint32_t pad[26];
+    uint32_t blocks_done;   // pass-1 CTAs that have published their partial sums (last one reduces)
+    uint32_t n_flagged;     // source tiles that receive far contributions (length of the flagged list)
+    uint32_t pad[24];
 };
 static_assert(sizeof(WsHeader) == 128, "header size");
 
 constexpr int kPartialSlots = 8;  // l1, gd, ssim, ce, tv_h, tv_w, n_valid(unused), spare
 
+// Final reduction of the per-CTA partial sums: fixed summation order (row index, then a fixed
+// tree), fp64 accumulation -> bitwise reproducible loss vector whatever the CTA schedule was.
+struct ReduceParams {
+    const float *partials;
+    int64_t n_blocks;
+    const WsHeader *hdr;
+    double inv_numel_rgb;   // 1/(Ng*3*H*W)
+    double inv_ssim;        // 1/(Ng*(H-2)*(W-2))
+    double inv_tvh, inv_tvw;
+    double ce_scale;        // N_local/N_global
+    float w_l1, w_gd, w_ssim, w_ce, w_tv;
+    float *out;
+};
+
+// Called by all 256 threads of one CTA; `s` is 6*256 doubles of shared memory.
+__device__ __forceinline__ void reduce_partials_block(const ReduceParams &p, double *s) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t b = threadIdx.x; b < p.n_blocks; b += 256) {
+        const float4 lo = __ldcg(reinterpret_cast<const float4 *>(p.partials + b * kPartialSlots));
+        const float2 hi = __ldcg(reinterpret_cast<const float2 *>(p.partials + b * kPartialSlots + 4));
+        acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w; acc[4] += hi.x; acc[5] += hi.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i * 256 + threadIdx.x] = acc[i];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s[i * 256 + threadIdx.x] += s[i * 256 + threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double nv = (double)__ldcg(&p.hdr->n_valid);
+        const double l1 = s[0] * p.inv_numel_rgb, gd = s[256] * p.inv_numel_rgb;
+        const double ssim = s[512] * p.inv_ssim;
+        const double ce = nv > 0 ? s[768] / nv * p.ce_scale : 0.0;
+        const double tv = s[1024] * p.inv_tvh + s[1280] * p.inv_tvw;
+        p.out[VLG_LOSS_L1] = (float)l1;
+        p.out[VLG_LOSS_GD] = (float)gd;
+        p.out[VLG_LOSS_SSIM] = (float)ssim;
+        p.out[VLG_LOSS_CE] = (float)ce;
+        p.out[VLG_LOSS_TV] = (float)tv;
+        const double tot = (double)p.w_l1 * l1 + (double)p.w_gd * gd + (double)p.w_ssim * ssim +
+                           (double)p.w_ce * ce + (double)p.w_tv * tv;
+        p.out[VLG_LOSS_TOTAL] = (float)tot;
+        p.out[VLG_LOSS_NVALID] = (float)nv;
+        p.out[VLG_LOSS_MAXDISP] = __uint_as_float(__ldcg(&p.hdr->maxdisp_bits));
+    }
+}
+
 struct WsLayout {
-    size_t header, tile_flags, partials, tile_disp, dout_rgb, dout_lay, far_acc, far_list, total;
+    size_t header, tile_flags, partials, tile_disp, flagged, dout_rgb, dout_lay, far_acc, far_list, total;
     int64_t n_blocks;
 };
 

@@ -50,6 +50,8 @@ struct Pass1Params {
     float *tile_disp;       // [n_blocks] max displacement among the tile's NEAR output pixels (WARP)
     int *far_list;          // [P] compacted indices of FAR output pixels (nullable: no source gradient / no far path)
     uint32_t *tile_flags;   // [n_blocks] != 0 where a far pixel lands in that SOURCE tile (zeroed with the header)
+    int *flagged_list;      // [n_blocks] compacted ids of the flagged source tiles
+    ReduceParams red;       // red.out != NULL: the last CTA also performs the final reduction
     WsHeader *hdr;
     uint32_t flags;
 };
@@ -72,6 +74,7 @@ struct Pass1Smem {
     int bbox[4];            // min x0, min y0, max x0, max y0 of the tile's own taps
     alignas(16) T stage[kSH * kSW * K];
 };
+static_assert(sizeof(float2) * 4 * kRN >= 6 * 256 * sizeof(double), "ab+flow must hold the final-reduction scratch");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -139,7 +142,10 @@ __device__ __forceinline__ float tap_global(const T *img, int C, int c, int y, i
 }
 
 template <typename T, int K, bool WARP>
-__global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
+#ifndef VLG_P1_MIN_BLOCKS
+#define VLG_P1_MIN_BLOCKS 3   // resident CTAs per SM the register allocation targets (smem allows 3)
+#endif
+__global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(const Pass1Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Pass1Smem<T, K> &sm = *reinterpret_cast<Pass1Smem<T, K> *>(smem_raw);
     const CoordCfg &cc = p.cc;
@@ -342,8 +348,11 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const int xx = t.x0 + (k4 & 1), yy = t.y0 + (k4 >> 1);
-                        if (xx >= 0 && xx < W && yy >= 0 && yy < H)
-                            atomicOr(&p.tile_flags[(n * p.tiles_y + yy / kTH) * p.tiles_x + xx / kTW], 1u);
+                        if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+                            const int tl = (n * p.tiles_y + yy / kTH) * p.tiles_x + xx / kTW;
+                            if (atomicOr(&p.tile_flags[tl], 1u) == 0u)
+                                p.flagged_list[atomicAdd(&p.hdr->n_flagged, 1u)] = tl;
+                        }
                     }
                 } else {
                     atomicOr(&p.hdr->status, VLG_STATUS_FAR_TAPS);
@@ -576,6 +585,21 @@ __global__ void __launch_bounds__(kThreads) pass1_kernel(const Pass1Params p) {
         if (WARP && p.tile_disp) p.tile_disp[bt] = nr;
         if (d > 0.f) atomicMax(&p.hdr->maxdisp_bits, __float_as_uint(d));
         if (g > 0.f) atomicMax(&p.hdr->maxgrad_bits, __float_as_uint(g));
+    }
+
+    // ---------------- phase 4: the last CTA to finish reduces all partial rows ----------------
+    // (replaces a separate 1-CTA reduction launch; the summation order is fixed by row index, so
+    // the result does not depend on which CTA happens to be last)
+    if (p.red.out != nullptr) {
+        __shared__ int s_last;
+        __threadfence();                 // publish this thread's partials / maxima
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&p.hdr->blocks_done, 1u) == gridDim.x * gridDim.y * gridDim.z - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            reduce_partials_block(p.red, reinterpret_cast<double *>(smem_raw));   // reuses sm.ab/flow (>= 12 KB)
+        }
     }
 }
 

@@ -30,6 +30,7 @@ struct Pass2Params {
     long long *far_acc;       // [P][3+K] fixed point, nullable (VLG_FLAG_NO_FAR_PATH)
     const int *far_list;      // [far_count] far output pixels queued by pass 1
     const uint32_t *tile_flags;  // [n_blocks] source tiles that receive far contributions
+    const int *flagged_list;  // [n_flagged] ids of those tiles
     const float *tile_disp;   // [n_blocks] per-tile max NEAR displacement written by pass 1
     WsHeader *hdr;
     int64_t HW;
@@ -60,7 +61,7 @@ __device__ __forceinline__ double far_scale(const WsHeader *hdr, int64_t HW) {
 
 template <int K>
 constexpr size_t pass2_smem_bytes() {
-    return (size_t)kQN * (sizeof(float2) + sizeof(float) * (3 + K));
+    return (size_t)kQN * (sizeof(float2) + sizeof(uint32_t) + sizeof(float) * (3 + K));
 }
 
 template <typename T, int K>
@@ -109,22 +110,31 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     if (tid < qw) s_bx[tid] = base_coord(tx0 - r + tid, cc.Wm1);
     else if (tid >= 64 && tid < 64 + qh) s_by[tid - 64] = base_coord(ty0 - r + tid - 64, cc.Hm1);
     __syncthreads();
+    // Each candidate output pixel is reduced to a packed integer cell code (x0 | y0 << 16, relative
+    // to the tile, biased by 8) plus its two fractional weights, so that the per-candidate test in
+    // the gather below is three integer instructions.
     const float2 *coords = reinterpret_cast<const float2 *>(p.coords) + img_px;
-    const float qnan = __int_as_float(0x7fc00000);
+    uint32_t *s_code = reinterpret_cast<uint32_t *>(s_rgb + (size_t)kQN * 3);   // [kQN]
     for (int ry = wid; ry < qh; ry += kThreads / 32) {
         const int y = ty0 - r + ry;
         for (int rx = lane; rx < qw; rx += 32) {
             const int x = tx0 - r + rx;
-            float2 xy = make_float2(qnan, qnan);
+            uint32_t code = 0xFFFFFFFFu;   // never matches
+            float2 frac = make_float2(0.f, 0.f);
             if (y >= 0 && y < H && x >= 0 && x < W) {
                 float mx, my;
                 const float2 s = source_xy(cc, __ldg(coords + (int64_t)y * W + x), s_bx[rx], s_by[ry], mx, my);
                 const float fx0 = floorf(s.x), fy0 = floorf(s.y);
                 const bool dead = fx0 < -1.0f || fx0 >= (float)W || fy0 < -1.0f || fy0 >= (float)H;  // no tap inside
                 const bool far = fmaxf(fabsf(s.x - (float)x), fabsf(s.y - (float)y)) >= (float)kRMax;
-                if (!far && !dead) xy = s;
+                if (!far && !dead) {
+                    // near => |x0 - x| <= kRMax, so the biased fields stay within [0, 2^15)
+                    code = (uint32_t)((int)fx0 - tx0 + 8) | ((uint32_t)((int)fy0 - ty0 + 8) << 16);
+                    frac = make_float2(__fsub_rn(s.x, fx0), __fsub_rn(s.y, fy0));
+                }
             }
-            s_xy[ry * qw + rx] = xy;
+            s_code[ry * qw + rx] = code;
+            s_xy[ry * qw + rx] = frac;
         }
     }
     cp_async_commit_wait_all();
@@ -137,18 +147,26 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     float acc_l[K], acc_r[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < K; ++k) acc_l[k] = 0.f;
-    const float fsx = (float)sx, fsy = (float)sy;
+    const uint32_t mycode = (uint32_t)(tx + 8) | ((uint32_t)(ty + 8) << 16);
     for (int dy = -r; dy <= r; ++dy) {
-        const int qrow = (ty + r + dy) * qw + tx + r;
-        for (int dx = -r; dx <= r; ++dx) {
-            const int q = qrow + dx;
-            const float2 xy = s_xy[q];
-            const float fx0 = floorf(xy.x), fy0 = floorf(xy.y);
-            const float ax = fsx - fx0, ay = fsy - fy0;   // 0 -> west/north tap, 1 -> east/south tap
-            const bool hit = (ax == 0.0f || ax == 1.0f) && (ay == 0.0f || ay == 1.0f);
-            if (!hit) continue;
-            const float wx = ax == 0.0f ? __fsub_rn(__fadd_rn(fx0, 1.0f), xy.x) : __fsub_rn(xy.x, fx0);
-            const float wy = ay == 0.0f ? __fsub_rn(__fadd_rn(fy0, 1.0f), xy.y) : __fsub_rn(xy.y, fy0);
+        const int qrow = (ty + r + dy) * qw + tx;   // candidate dx = -r sits at qrow, dx = +r at qrow + 2r
+        // e = (sx - x0) + ((sy - y0) << 16): a hit iff both differences are 0 (west/north tap)
+        // or 1 (east/south tap); any other difference (incl. borrows) leaves a bit outside {0,16}.
+        // All codes of the row are fetched first (independent LDS) -- the kernel is latency-bound.
+        uint32_t ev[2 * kRMax + 1];
+#pragma unroll
+        for (int j = 0; j < 2 * kRMax + 1; ++j) ev[j] = (j <= 2 * r) ? mycode - s_code[qrow + j] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < 2 * kRMax + 1; ++j) {
+            const uint32_t e = ev[j];
+            if (e & 0xFFFEFFFEu) continue;
+            const int q = qrow + j;
+            const float2 f = s_xy[q];
+            // tap weights: east/south = frac, west/north = 1 - frac, which is bit-identical to the
+            // forward's (x0 + 1) - ix for every in-image tap (both are exact for x0 >= 1, and the
+            // same expression for x0 == 0)
+            const float wx = (e & 1u) ? f.x : __fsub_rn(1.0f, f.x);
+            const float wy = (e >> 16) ? f.y : __fsub_rn(1.0f, f.y);
             const float w = __fmul_rn(wx, wy);
             if (want_lay) {
                 float v[K];
@@ -177,11 +195,10 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
 // ---- far path: zero the fixed-point accumulators of the flagged source tiles only ----
 template <int K>
 __global__ void __launch_bounds__(kThreads) far_zero_kernel(const Pass2Params p) {
-    if (p.hdr->far_count == 0) return;
-    const int n_tiles = p.N * p.tiles_y * p.tiles_x;
+    const int n_flagged = (int)p.hdr->n_flagged;
     const int ty = threadIdx.x / kTW, tx = threadIdx.x - ty * kTW;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (!p.tile_flags[t]) continue;
+    for (int i = blockIdx.x; i < n_flagged; i += gridDim.x) {
+        const int t = p.flagged_list[i];
         const int n = t / (p.tiles_y * p.tiles_x), rem = t - n * (p.tiles_y * p.tiles_x);
         const int y = (rem / p.tiles_x) * kTH + ty, x = (rem % p.tiles_x) * kTW + tx;
         if (y >= p.cc.H || x >= p.cc.W) continue;
@@ -192,39 +209,41 @@ __global__ void __launch_bounds__(kThreads) far_zero_kernel(const Pass2Params p)
 }
 
 // ---- far path: fixed-point scatter of the queued far output pixels ----
+// one thread per (far pixel, tap, channel): the integer atomics are associative, so neither the
+// queue order nor the thread schedule can change the sums.
 template <int K>
 __global__ void far_scatter_kernel(const Pass2Params p) {
     const unsigned n_far = p.hdr->far_count;
     if (n_far == 0) return;
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
+    constexpr unsigned PER_PX = 4u * (3 + K);
     const double scale = far_scale(p.hdr, p.HW);
     const float2 *coords = reinterpret_cast<const float2 *>(p.coords);
-    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n_far; j += gridDim.x * blockDim.x) {
+    const unsigned long long total = (unsigned long long)n_far * PER_PX;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned j = (unsigned)(w / PER_PX), rem4 = (unsigned)(w - (unsigned long long)j * PER_PX);
+        const int k4 = (int)(rem4 / (3 + K)), c = (int)(rem4 - k4 * (3 + K));
         const int64_t i = p.far_list[j];
         const int64_t n = i / p.HW;
         const int64_t rem = i - n * p.HW;
         const int y = (int)(rem / W), x = (int)(rem - (int64_t)y * W);
         const Taps t = make_taps(cc, __ldg(coords + i), y, x);
-        const int xs[4] = {t.x0, t.x0 + 1, t.x0, t.x0 + 1};
-        const int ys[4] = {t.y0, t.y0, t.y0 + 1, t.y0 + 1};
-        const float ws[4] = {t.nw, t.ne, t.sw, t.se};
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-            if (xs[k4] < 0 || xs[k4] >= W || ys[k4] < 0 || ys[k4] >= H) continue;
-            unsigned long long *dst = reinterpret_cast<unsigned long long *>(
-                p.far_acc + (n * p.HW + (int64_t)ys[k4] * W + xs[k4]) * (3 + K));
-            if (p.d_out_rgb)
-                for (int c = 0; c < 3; ++c) {
-                    const long long v = __double2ll_rn((double)__fmul_rn(ws[k4], __ldg(p.d_out_rgb + i * 3 + c)) * scale);
-                    atomicAdd(dst + c, (unsigned long long)v);
-                }
-            if (p.d_out_lay)
-                for (int c = 0; c < K; ++c) {
-                    const long long v = __double2ll_rn((double)__fmul_rn(ws[k4], __ldg(p.d_out_lay + i * K + c)) * scale);
-                    atomicAdd(dst + 3 + c, (unsigned long long)v);
-                }
+        const int xs = t.x0 + (k4 & 1), ys = t.y0 + (k4 >> 1);
+        if (xs < 0 || xs >= W || ys < 0 || ys >= H) continue;
+        const float wt = k4 == 0 ? t.nw : k4 == 1 ? t.ne : k4 == 2 ? t.sw : t.se;
+        float d;
+        if (c < 3) {
+            if (!p.d_out_rgb) continue;
+            d = __ldg(p.d_out_rgb + i * 3 + c);
+        } else {
+            if (!p.d_out_lay) continue;
+            d = __ldg(p.d_out_lay + i * K + (c - 3));
         }
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(
+            p.far_acc + (n * p.HW + (int64_t)ys * W + xs) * (3 + K) + c);
+        atomicAdd(dst, (unsigned long long)__double2ll_rn((double)__fmul_rn(wt, d) * scale));
     }
 }
 
