@@ -333,3 +333,45 @@ def test_linearity_of_source_gradient_transpose():
     rhs = (gout.double() * o_rgb.double()).sum().item()
     assert abs(lhs - rhs) <= 1e-5 * abs(rhs)
     assert b.grad.abs().max().item() == 0.0   # w_ce = 0 -> no layout gradient
+
+
+# ------------------------------------------------------------------ bf16 activations (BASELINE config 3)
+def test_bf16_io_within_1e2():
+    """bf16 inputs/outputs, fp32 flow and accumulation: losses and gradients within 1e-2 of the fp32
+    oracle evaluated on the SAME bf16-rounded inputs (north_star tolerance for bf16)."""
+    d = _make_case(2, 64, 96, 20, 2.0, seed=9, layout="soft")
+    bf = lambda t: t.to(torch.bfloat16)
+    src_rgb, src_lay, tgt = bf(d["src_rgb"]), bf(d["src_layout"]), bf(d["tgt_rgb"])
+    ref = TO.warp_loss_fwd_bwd(src_rgb.float(), src_lay.float(), d["flow"], tgt.float(), d["tgt_label"], w_tv=0.5)
+    a = _cl(src_rgb).requires_grad_(True)
+    b = _cl(src_lay).requires_grad_(True)
+    f = d["flow"].to(DEV).requires_grad_(True)
+    total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(tgt), d["tgt_label"].to(DEV),
+                                         vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
+    total.backward()
+    got = vec.cpu().numpy().astype(np.float64)
+    want = np.array([ref["terms"][k].item() for k in TERMS])
+    np.testing.assert_allclose(got[:5], want, rtol=1e-2)
+    assert a.grad.dtype == torch.bfloat16 and b.grad.dtype == torch.bfloat16 and f.grad.dtype == torch.float32
+    _assert_close_norm(_nchw(f.grad), ref["d_flow"].numpy(), 1e-2, "d_flow")
+    _assert_close_norm(_nchw(a.grad), ref["d_src_rgb"].numpy(), 1e-2, "d_src_rgb")
+    _assert_close_norm(_nchw(b.grad), ref["d_src_layout"].numpy(), 1e-2, "d_src_layout")
+    # forward warp in bf16: same taps, values rounded once at the store
+    o_rgb, o_lay, o_arg = vlg_b200.warp(a.detach(), b.detach(), f.detach())
+    assert o_lay.dtype == torch.bfloat16
+    want_lay = ref["warped_layout"].detach().to(torch.bfloat16)
+    assert torch.equal(o_lay.cpu().contiguous(), want_lay.contiguous())
+
+
+def test_full_res_forward_config3_properties():
+    """8x1024x2048 is too large for the CPU oracle; check the forward-only path against torch CUDA
+    grid_sample on one full-resolution image (src/val.py:172-176 shape) in fp32, bit for bit."""
+    N, H, W, K = 1, 1024, 2048, 20
+    d = _make_case(N, H, W, K, 4.0, seed=31)
+    a, b, f = _cl(d["src_rgb"]), _cl(d["src_layout"]), d["flow"].to(DEV)
+    o_rgb, o_lay, o_arg = vlg_b200.warp(a, b, f)
+    grid = TO.flow_to_grid(f)
+    r_lay = TO.warp(d["src_layout"].to(DEV), grid)
+    assert torch.equal(o_lay.contiguous(), r_lay.contiguous())
+    assert torch.equal(o_arg, torch.argmax(r_lay, 1))
+    assert tuple(o_arg.shape) == (N, 1024, 2048)
