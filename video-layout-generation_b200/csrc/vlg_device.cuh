@@ -80,6 +80,15 @@ __device__ __forceinline__ void reduce_partials_block(const ReduceParams &p, dou
     }
 }
 
+// Layout of the d(loss)/d(warped layout) staging buffer between pass 1 and pass 2: chunk-planar,
+// [n][K/CPC][H*W][CPC] with CPC = 4 channels (one 128-bit word) when K % 4 == 0, else 1.
+template <int K> __host__ __device__ constexpr int dout_cpc() { return K % 4 == 0 ? 4 : 1; }
+template <int K>
+__host__ __device__ __forceinline__ int64_t dout_index(int64_t n, int64_t HW, int64_t px, int k) {
+    constexpr int CPC = dout_cpc<K>();
+    return ((n * (K / CPC) + k / CPC) * HW + px) * CPC + k % CPC;
+}
+
 struct WsLayout {
     size_t header, tile_flags, partials, tile_disp, flagged, dout_rgb, dout_lay, far_acc, far_list, total;
     int64_t n_blocks;

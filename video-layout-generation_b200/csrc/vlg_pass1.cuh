@@ -56,9 +56,18 @@ struct Pass1Params {
     uint32_t flags;
 };
 
-// staged source-layout window (pixels); covers the tile's taps for displacement spreads up to
-// +-3 px horizontally and +-1 px vertically around the tile's mean motion
+#ifndef VLG_P1_MIN_BLOCKS
+#define VLG_P1_MIN_BLOCKS 3   // resident CTAs per SM the register / shared-memory budget targets
+#endif
+// staged source-layout window (pixels); covers the tile's taps for displacement spreads of a few
+// pixels around the tile's mean motion; pixels whose taps fall outside use the global path
+#if VLG_P1_MIN_BLOCKS >= 4
+constexpr int kSW = 36, kSH = 10;   // 28.8 KB (K=20 fp32): 4 CTAs of <= 56 KB fit one SM
+#define VLG_P1_FLOW_IN_SMEM 0
+#else
 constexpr int kSW = 40, kSH = 12;
+#define VLG_P1_FLOW_IN_SMEM 1
+#endif
 constexpr int kSegW = 5;                               // SSIM windows per run
 constexpr int kSegs = (kWW + kSegW - 1) / kSegW;       // 7 runs per window row
 static_assert(kSegs * kWH * 3 <= kThreads, "one SSIM run per thread");
@@ -66,15 +75,19 @@ static_assert(kSegs * kWH * 3 <= kThreads, "one SSIM run per thread");
 template <typename T, int K>
 struct Pass1Smem {
     float2 ab[3][kRN];      // (warped-or-given rgb, target rgb) over the tile + halo 2
+#if VLG_P1_FLOW_IN_SMEM
     float2 flow[kRN];       // raw coords (TV stencil, tap recomputation)
-    float4 k[3][kWN];       // per-window SSIM adjoint coefficients (A,B,C,-)
+#endif
+    float2 kab[3][kWN];     // per-window SSIM adjoint coefficients (A,B) ...
+    float kc[3][kWN];       // ... and C (12 bytes per window: fewer smem wavefronts than a padded float4)
     float bx[kRW], by[kRH]; // base-grid coordinates of the region's columns / rows
     float red[kThreads / 32][kPartialSlots];
     float redmax[kThreads / 32][4];
     int bbox[4];            // min x0, min y0, max x0, max y0 of the tile's own taps
     alignas(16) T stage[kSH * kSW * K];
 };
-static_assert(sizeof(float2) * 4 * kRN >= 6 * 256 * sizeof(double), "ab+flow must hold the final-reduction scratch");
+static_assert(sizeof(float2) * 3 * kRN + sizeof(float) * 9 * kWN >= 6 * 256 * sizeof(double),
+              "ab (+flow) + k must hold the final-reduction scratch");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -142,9 +155,6 @@ __device__ __forceinline__ float tap_global(const T *img, int C, int c, int y, i
 }
 
 template <typename T, int K, bool WARP>
-#ifndef VLG_P1_MIN_BLOCKS
-#define VLG_P1_MIN_BLOCKS 3   // resident CTAs per SM the register allocation targets (smem allows 3)
-#endif
 __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(const Pass1Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Pass1Smem<T, K> &sm = *reinterpret_cast<Pass1Smem<T, K> *>(smem_raw);
@@ -212,7 +222,9 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
 #pragma unroll
                     for (int c = 0; c < 3; ++c) sm.ab[c][q] = make_float2(a[c], b[c]);
                 }
+#if VLG_P1_FLOW_IN_SMEM
                 if (WARP) sm.flow[q] = fl;
+#endif
             }
         }
         if (WARP && has_lay) {
@@ -319,7 +331,8 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                             kk4.x = kk * (m2.y * (n2 - n1) * r + S * m2.x * (inv_d2 - inv_d1));
                         }
                     }
-                    sm.k[c][wy * kWW + wx] = kk4;
+                    sm.kab[c][wy * kWW + wx] = make_float2(kk4.x, kk4.y);
+                    sm.kc[c][wy * kWW + wx] = kk4.z;
                 }
             }
         }
@@ -337,7 +350,12 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         Taps t;
         if (WARP) {
             float mx, my;
-            const float2 xy = source_xy(cc, sm.flow[q0], sm.bx[tx + kHalo], sm.by[ty + kHalo], mx, my);
+#if VLG_P1_FLOW_IN_SMEM
+#define VLG_FLOW_AT(dq, doff) sm.flow[q0 + (dq)]
+#else
+#define VLG_FLOW_AT(dq, doff) __ldg(coords + o + (doff))
+#endif
+            const float2 xy = source_xy(cc, VLG_FLOW_AT(0, 0), sm.bx[tx + kHalo], sm.by[ty + kHalo], mx, my);
             t = taps_from_xy(cc, xy, mx, my);
             m_disp = tap_displacement(cc, t, y, x);
             m_near = m_disp < (float)VLG_NEAR_RADIUS ? m_disp : 0.0f;
@@ -403,14 +421,14 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                     // SSIM adjoint: the <=9 windows whose footprint contains this pixel
                     float2 sAB = make_float2(0.f, 0.f);
                     float sC = 0.f;
-                    const float4 *kp = &sm.k[c][ty * kWW + tx];
+                    const float2 *kab = &sm.kab[c][ty * kWW + tx];
+                    const float *kc = &sm.kc[c][ty * kWW + tx];
 #pragma unroll
                     for (int di = 0; di < 3; ++di)
 #pragma unroll
                         for (int dj = 0; dj < 3; ++dj) {
-                            const float4 kk = kp[di * kWW + dj];
-                            sAB = __fadd2_rn(sAB, make_float2(kk.x, kk.y));
-                            sC += kk.z;
+                            sAB = __fadd2_rn(sAB, kab[di * kWW + dj]);
+                            sC += kc[di * kWW + dj];
                         }
                     g += fmaf(sC, b, fmaf(sAB.y, a, sAB.x));
                 }
@@ -507,6 +525,8 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                         coord_grad_px<T, K>(src_lay, cc, t, gfull, gix, giy);
                     }
                     if (p.d_out_lay) {
+                        // (a chunk-planar staging layout makes these stores coalesced, -10 us here, but
+                        // costs pass 2 +27 us in strided cp.async runs: measured, rejected)
                         float *dst = reinterpret_cast<float *>(p.d_out_lay) + (img_px + o) * K;
                         store_px<float, K>(dst, z);
                         if (lab_ok) dst[il] = gl;
@@ -522,26 +542,26 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         if (WARP) {
             float gx = t.mx * gix, gy = t.my * giy;
             if (p.do_tv) {
-                const float2 f = sm.flow[q0];
+                const float2 f = VLG_FLOW_AT(0, 0);
                 if (y + 1 < H) {
-                    const float2 df = __fadd2_rn(sm.flow[q0 + kRW], make_float2(-f.x, -f.y));
+                    const float2 df = __fadd2_rn(VLG_FLOW_AT(kRW, W), make_float2(-f.x, -f.y));
                     s_tvh += fabsf(df.x) + fabsf(df.y);
                     gx -= signed_c1(p.c_tvh, df.x);
                     gy -= signed_c1(p.c_tvh, df.y);
                 }
                 if (y >= 1) {
-                    const float2 f1 = sm.flow[q0 - kRW];
+                    const float2 f1 = VLG_FLOW_AT(-kRW, -W);
                     gx += signed_c1(p.c_tvh, f.x - f1.x);
                     gy += signed_c1(p.c_tvh, f.y - f1.y);
                 }
                 if (x + 1 < W) {
-                    const float2 df = __fadd2_rn(sm.flow[q0 + 1], make_float2(-f.x, -f.y));
+                    const float2 df = __fadd2_rn(VLG_FLOW_AT(1, 1), make_float2(-f.x, -f.y));
                     s_tvw += fabsf(df.x) + fabsf(df.y);
                     gx -= signed_c1(p.c_tvw, df.x);
                     gy -= signed_c1(p.c_tvw, df.y);
                 }
                 if (x >= 1) {
-                    const float2 f1 = sm.flow[q0 - 1];
+                    const float2 f1 = VLG_FLOW_AT(-1, -1);
                     gx += signed_c1(p.c_tvw, f.x - f1.x);
                     gy += signed_c1(p.c_tvw, f.y - f1.y);
                 }

@@ -143,12 +143,12 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     // ---- one thread per source pixel: fixed-order gather ----
     const int ty = tid / kTW, tx = tid - ty * kTW;
     const int sy = ty0 + ty, sx = tx0 + tx;
-    if (sy >= H || sx >= W) return;
+    const bool live = sy < H && sx < W;
     float acc_l[K], acc_r[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < K; ++k) acc_l[k] = 0.f;
     const uint32_t mycode = (uint32_t)(tx + 8) | ((uint32_t)(ty + 8) << 16);
-    for (int dy = -r; dy <= r; ++dy) {
+    for (int dy = live ? -r : r + 1; dy <= r; ++dy) {
         const int qrow = (ty + r + dy) * qw + tx;   // candidate dx = -r sits at qrow, dx = +r at qrow + 2r
         // e = (sx - x0) + ((sy - y0) << 16): a hit iff both differences are 0 (west/north tap)
         // or 1 (east/south tap); any other difference (incl. borrows) leaves a bit outside {0,16}.
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
         }
     }
     const int64_t so = img_px + (int64_t)sy * W + sx;
-    if (p.far_acc && p.tile_flags[bt]) {
+    if (live && p.far_acc && p.tile_flags[bt]) {
         const double inv = 1.0 / far_scale(p.hdr, p.HW);
         const long long *fa = p.far_acc + so * (3 + K);
 #pragma unroll
@@ -188,8 +188,29 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
 #pragma unroll
         for (int k = 0; k < K; ++k) acc_l[k] += (float)((double)fa[3 + k] * inv);
     }
-    if (want_rgb) store_px<T, 3>(reinterpret_cast<T *>(p.d_src_rgb) + so * 3, acc_r);
-    if (want_lay) store_px<T, K>(reinterpret_cast<T *>(p.d_src_lay) + so * K, acc_l);
+    if (live && want_rgb) store_px<T, 3>(reinterpret_cast<T *>(p.d_src_rgb) + so * 3, acc_r);
+    if (want_lay) {
+        // A thread-per-pixel store of 80-byte pixels costs 20 L1 wavefronts per 128-bit store
+        // instruction; transposing through shared memory lets each warp write its tile row
+        // (32 px x K, contiguous in HBM) as consecutive 16-byte words: 4 wavefronts each.
+        __syncthreads();                                   // all gathers done: the d_out staging can be reused
+        T *s_out = reinterpret_cast<T *>(s_lay);           // [kThreads][K]
+        if (live) store_px<T, K>(s_out + (size_t)tid * K, acc_l);
+        __syncwarp();
+        const int sy_w = ty0 + wid;                        // warp w owns tile row w (kTW == 32)
+        if (sy_w < H) {
+            const int npx = min(kTW, W - tx0);
+            T *grow = reinterpret_cast<T *>(p.d_src_lay) + (img_px + (int64_t)sy_w * W + tx0) * K;
+            const T *srow = s_out + (size_t)wid * kTW * K;
+            if constexpr ((K * sizeof(T)) % 16 == 0) {
+                const int nvec = npx * (int)(K * sizeof(T) / 16);
+                for (int i = lane; i < nvec; i += 32)
+                    reinterpret_cast<uint4 *>(grow)[i] = reinterpret_cast<const uint4 *>(srow)[i];
+            } else {
+                for (int i = lane; i < npx * K; i += 32) grow[i] = srow[i];
+            }
+        }
+    }
 }
 
 // ---- far path: zero the fixed-point accumulators of the flagged source tiles only ----
