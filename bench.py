@@ -137,6 +137,10 @@ def run_reference(args, rank, world):
     N, H, W, K, sigma, far, dtype = WORKLOADS[args.workload]
     n_sample = min(N, 2)
     ts = []
+    try:   # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread it may
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     from oracle import torch_oracle as TO
     d = make_inputs(n_sample, H, W, K, sigma, far, "f32", None)
     for i in range(args.warmup + args.steps):
@@ -165,6 +169,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip timing the torch CUDA eager incumbent")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (iters/s) measurement")
     ap.add_argument("--flow-grad-only", action="store_true", help="sources are data: no d_src (128 B/px variant)")
     args = ap.parse_args()
 
@@ -299,6 +305,36 @@ def main():
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
 
+    # ---- incumbent on the same GPU: the oracle composition run by torch CUDA eager (ATen kernels) ----
+    eager = None
+    if rank == 0 and dtype == "f32" and not args.no_eager:
+        from oracle import torch_oracle as TO
+        s0 = sets[0]
+        def eager_step():
+            a = s0["src_rgb"].detach().requires_grad_(with_src)
+            b = s0["src_layout"].detach().requires_grad_(with_src)
+            f = s0["flow"].detach().requires_grad_(True)
+            o = TO.warp_loss(a, b, f, s0["tgt_rgb"], s0["tgt_label"], w_tv=0.5)
+            o["total"].backward()
+        for _ in range(2):
+            eager_step()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(5):
+            eager_step()
+        g1.record(stream)
+        torch.cuda.synchronize()
+        ms_eager = g0.elapsed_time(g1) / 5
+        eager = {"ms_per_step": ms_eager, "value": P / (ms_eager * 1e-3) / 1e6, "unit": "Mpixel/s",
+                 "what": "oracle composition (F.grid_sample + losses + autograd) in torch CUDA eager, same inputs, checker only"}
+
+    # ---- training step: torch flow producer -> fused op -> DDP -> Adam, iters/s ----
+    train = None
+    if args.workload == "c2" and not args.no_train:
+        from train import run_training
+        train, _ = run_training(steps=max(3, min(args.steps, 10)), warmup=2, batch=N, height=H, width=W, classes=K)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -334,6 +370,8 @@ def main():
                 "d2h_bytes_per_step": _cabi.LOSS_SLOTS * 4, "ms_per_step": t_e2e.item()},
         "gpu_launches": launches,
         "clocks": clocks,
+        "train": train,
+        "torch_cuda_eager": eager,
     }
     if world == 1 and not args.no_cpu_baseline:
         n_sample = min(N, 4)
