@@ -117,6 +117,14 @@ int vlg_warp_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src
                  const float *coords, void *out_rgb, void *out_layout, int64_t *out_argmax,
                  int32_t *dbg_x0y0, void *stream);
 
+/* Rollout warp with LABEL sources (autoregressive feedback of src/trainer.py:460-469: the layout fed
+ * back is argmax -> one-hot, so the K-channel gather collapses to four int64 taps):
+ *   out_rgb   [N,H,W,3]   = warp(src_rgb)                                   (nullable with src_rgb)
+ *   out_label [N,H,W] i64 = argmax_k warp(one_hot(src_label))_k, bit-exact with the dense path
+ * prob->K is only validated, not used. */
+int vlg_warp_fwd_labels(const vlg_problem_t *prob, const void *src_rgb, const int64_t *src_label,
+                        const float *coords, void *out_rgb, int64_t *out_label, void *stream);
+
 /* Pass 1 of the fused op: warp + all loss terms + d(loss)/d(warped) + d(loss)/d(coords) in one
  * kernel.  Gradients are for an upstream grad of 1.0 (see vlg_scale_grads).
  *   tgt_rgb [N,H,W,3], tgt_label [N,H,W] i64

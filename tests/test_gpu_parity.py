@@ -375,3 +375,39 @@ def test_full_res_forward_config3_properties():
     assert torch.equal(o_lay.contiguous(), r_lay.contiguous())
     assert torch.equal(o_arg, torch.argmax(r_lay, 1))
     assert tuple(o_arg.shape) == (N, 1024, 2048)
+
+
+# ------------------------------------------------------------------ rollout with label sources
+@pytest.mark.parametrize("padding", ["border", "zeros"])
+def test_label_source_warp_matches_dense_one_hot(padding):
+    """warp_labels(label) == argmax(warp(one_hot(label))) bit for bit, including half-pixel ties."""
+    K = 20
+    for seed, sigma, half in ((3, 2.0, False), (4, 3.0, True), (5, 30.0, False)):
+        d = _make_case(2, 61, 93, K, sigma, seed=seed)
+        flow = d["flow"]
+        if half:
+            flow = torch.round(flow * 2) / 2          # exact ties between classes
+        lab = d["src_layout"].argmax(1)
+        f = flow.to(DEV)
+        o_rgb, _, o_arg = vlg_b200.warp(_cl(d["src_rgb"]), _cl(d["src_layout"]), f, padding_mode=padding)
+        l_rgb, l_lab = vlg_b200.warp_labels(_cl(d["src_rgb"]), lab.to(DEV), f, padding_mode=padding)
+        assert torch.equal(l_lab, o_arg)
+        assert torch.equal(l_rgb, o_rgb)
+        ref = TO.warp(d["src_layout"], TO.flow_to_grid(flow), padding)
+        assert torch.equal(l_lab.cpu(), TO.argmax_layout(ref))
+
+
+def test_rollout_five_steps_matches_dense_feedback():
+    """5-step autoregressive rollout (BASELINE config 4 shape, reduced): label feedback equals the
+    dense argmax -> one-hot -> warp loop of src/trainer.py:460-469 at every step."""
+    K, steps = 20, 5
+    d = _make_case(2, 64, 128, K, 3.0, seed=17)
+    flows = [(_make_case(2, 64, 128, K, 3.0, seed=100 + t)["flow"]).to(DEV) for t in range(steps)]
+    img0, lab0 = _cl(d["src_rgb"]), d["src_layout"].argmax(1).to(DEV)
+    imgs, labs = vlg_b200.rollout(img0, lab0, lambda t, i, l: flows[t], steps=steps)
+    img, lay = img0, _cl(d["src_layout"])
+    for t in range(steps):
+        img, _, arg = vlg_b200.warp(img, lay, flows[t])
+        lay = torch.zeros_like(lay).scatter_(1, arg[:, None], 1.0)     # argmax -> one-hot feedback
+        assert torch.equal(labs[t], arg), t
+        assert torch.equal(imgs[t], img), t

@@ -137,6 +137,52 @@ __global__ void scale_kernel(T *g, int64_t n, const float *scale) {
         g[i] = from_f<T>(to_f<T>(g[i]) * s);
 }
 
+// Rollout warp with LABEL sources: the layout fed back between rollout steps is
+// argmax -> one-hot (src/trainer.py:467), so the 20-channel gather collapses to four int64 taps.
+// out_label == argmax_c warp(one_hot(src_label))_c bit for bit: for a 0/1 source the dense FMA
+// chain reduces to adding the weights of the taps that carry class c, in tap order nw,ne,sw,se.
+template <typename T>
+__global__ void __launch_bounds__(256) warp_fwd_labels_kernel(CoordCfg cc, int64_t P, int64_t HW, const T *__restrict__ src_rgb,
+                                                              const int64_t *__restrict__ src_label,
+                                                              const float2 *__restrict__ coords, T *out_rgb,
+                                                              int64_t *out_label) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int64_t n = i / HW, rem = i - n * HW;
+    const int y = (int)(rem / cc.W), x = (int)(rem - (int64_t)y * cc.W);
+    const Taps t = make_taps(cc, __ldg(coords + i), y, x);
+    if (src_rgb && out_rgb) {
+        float a[3];
+        gather_px<T, 3>(src_rgb + n * HW * 3, cc, t, a);
+        store_px<T, 3>(out_rgb + i * 3, a);
+    }
+    if (src_label && out_label) {
+        const int xs[4] = {t.x0, t.x0 + 1, t.x0, t.x0 + 1};
+        const int ys[4] = {t.y0, t.y0, t.y0 + 1, t.y0 + 1};
+        const float ws[4] = {t.nw, t.ne, t.sw, t.se};
+        int64_t lab[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool in = xs[k] >= 0 && xs[k] < cc.W && ys[k] >= 0 && ys[k] < cc.H;
+            lab[k] = in ? __ldg(src_label + n * HW + (int64_t)ys[k] * cc.W + xs[k]) : (int64_t)-1;   // -1: contributes nothing
+        }
+        float best_z = 0.0f;          // classes carried by no tap have z == 0; the first of them is class 0
+        int64_t best_c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t c = lab[k];
+            if (c < 0) continue;
+            // z_c through the same chain as the dense path: fmul for the nw tap, then three fmas
+            float z = __fmul_rn(lab[0] == c ? 1.0f : 0.0f, ws[0]);
+            z = __fmaf_rn(lab[1] == c ? 1.0f : 0.0f, ws[1], z);
+            z = __fmaf_rn(lab[2] == c ? 1.0f : 0.0f, ws[2], z);
+            z = __fmaf_rn(lab[3] == c ? 1.0f : 0.0f, ws[3], z);
+            if (z > best_z || (z == best_z && c < best_c)) { best_z = z; best_c = c; }
+        }
+        out_label[i] = best_c;
+    }
+}
+
 // forward-only warp (validation / rollout): one thread per output pixel
 template <typename T, int K>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, int64_t HW, const T *__restrict__ src_rgb,
@@ -311,6 +357,25 @@ int vlg_warp_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src
     VLG_FOR_EACH_K(X)
 #undef X
     return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
+}
+
+int vlg_warp_fwd_labels(const vlg_problem_t *prob, const void *src_rgb, const int64_t *src_label, const float *coords,
+                        void *out_rgb, int64_t *out_label, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if (!coords) return fail(VLG_ERR_ARG, "coords is NULL");
+    if ((src_label == nullptr) != (out_label == nullptr)) return fail(VLG_ERR_ARG, "src_label and out_label go together");
+    const int64_t HW = prob->H * prob->W, P = prob->N * HW;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((P + 255) / 256);
+    if (prob->dtype == VLG_F32)
+        warp_fwd_labels_kernel<float><<<blocks, 256, 0, st>>>(make_cc(prob), P, HW, (const float *)src_rgb, src_label,
+                                                              (const float2 *)coords, (float *)out_rgb, out_label);
+    else
+        warp_fwd_labels_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(make_cc(prob), P, HW, (const __nv_bfloat16 *)src_rgb,
+                                                                      src_label, (const float2 *)coords,
+                                                                      (__nv_bfloat16 *)out_rgb, out_label);
+    return check_launch("warp_fwd_labels_kernel");
 }
 
 static int warp_loss_pass1(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,

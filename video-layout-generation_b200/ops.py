@@ -135,6 +135,42 @@ def warp(src_rgb: Optional[torch.Tensor], src_layout: Optional[torch.Tensor], co
     return res + (dbg,) if debug_indices else res
 
 
+@torch.no_grad()
+def warp_labels(src_rgb: Optional[torch.Tensor], src_label: torch.Tensor, coords: torch.Tensor, *,
+                padding_mode: str = "border", coords_are_grid: bool = False):
+    """Rollout warp with an integer label map as the layout source: returns (warped_rgb | None,
+    warped_label int64 [N,H,W]) where warped_label == argmax(warp(one_hot(src_label))) bit for bit,
+    at 8 B/px of layout traffic instead of 80."""
+    lib = _cabi.load()
+    _require_cuda(src_rgb, src_label, coords)
+    if src_label.dtype != torch.int64 or src_label.dim() != 3:
+        raise VlgError("src_label must be int64 [N,H,W]")
+    N, H, W = src_label.shape
+    dt = src_rgb.dtype if src_rgb is not None else torch.float32
+    prob = _problem(N, H, W, 20, dt, WarpLossConfig(padding_mode=padding_mode, coords_are_grid=coords_are_grid))
+    coords = _coords(coords, N, H, W)
+    a = to_nhwc(src_rgb) if src_rgb is not None else None
+    lab = src_label.contiguous()
+    out_rgb = empty_nhwc((N, 3, H, W), dt, lab.device) if a is not None else None
+    out_lab = torch.empty_like(lab)
+    check(lib.vlg_warp_fwd_labels(C.byref(prob), _ptr(a), _ptr(lab), _ptr(coords), _ptr(out_rgb), _ptr(out_lab), _stream()))
+    return out_rgb, out_lab
+
+
+@torch.no_grad()
+def rollout(img: torch.Tensor, label: torch.Tensor, flow_fn, steps: int = 5, *, padding_mode: str = "border"):
+    """Autoregressive rollout (shape of src/trainer.py:453-476, which runs 8 steps and feeds the
+    argmax back): step t warps the previous frame and label map with `flow_fn(t, img, label)`
+    ([N,H,W,2] pixels) and feeds both back.  Returns (list of frames, list of label maps)."""
+    imgs, labels = [img], [label]
+    for t in range(steps):
+        flow = flow_fn(t, imgs[-1], labels[-1])
+        nxt_img, nxt_lab = warp_labels(imgs[-1], labels[-1], flow, padding_mode=padding_mode)
+        imgs.append(nxt_img)
+        labels.append(nxt_lab)
+    return imgs[1:], labels[1:]
+
+
 # --------------------------------------------------------------------------- fused warp + loss
 class _WarpLossFn(torch.autograd.Function):
     """Fused forward+backward: the gradients are produced by the SAME pass as the losses (for an
