@@ -350,6 +350,14 @@ def main():
     value = world * P / (ms_per_step * 1e-3) / 1e6
     dom_name, dom_ms, dom_bytes = ("pass1_kernel", k1, bpp["pass1"]) if (k1 >= k2 or not with_src) else ("pass2_kernel", k2, bpp["pass2"])
     achieved = P * dom_bytes / (dom_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full`
+    # capture of this same workload (profiles/r01_ncu_traffic.json); null for other workloads
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if args.workload == "c2" and with_src and os.path.exists(tpath):
+        k = json.load(open(tpath))["kernels"].get(dom_name)
+        if k:
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     out = {
         "metric": "warp+loss fwd/bwd throughput", "value": value, "unit": "Mpixel/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -360,7 +368,8 @@ def main():
                    "l2_policy": "inputs (%.0f MB/step) exceed the 126 MB L2; two input sets alternate" % (P * 120 / 1e6),
                    "parallelism": f"dp{world}"},
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes": P * dom_bytes,
                      "algorithmic_bytes_per_px": dom_bytes, "kernel_ms": dom_ms},
         "roofline_step": {"algorithmic_bytes_per_px": step_bytes,
                           "achieved": P * step_bytes / (ms_per_step * 1e-3) / 1e9,
