@@ -177,6 +177,16 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
     float s_l1 = 0.f, s_gd = 0.f, s_ssim = 0.f, s_ce = 0.f, s_tvh = 0.f, s_tvw = 0.f;
     float m_disp = 0.f, m_near = 0.f, m_grad = 0.f;
 
+    // Loads whose consumers sit in phase 2 are issued now, so that their (L2/DRAM) latency is
+    // hidden behind phases 0-1 instead of stalling the longest phase.
+    int64_t lab_pre = 0;
+    unsigned long long nvalid_pre = 0;
+    {
+        const int py = ty0 + tid / kTW, px = tx0 + (tid & (kTW - 1));
+        if (has_lay && py < H && px < W) lab_pre = __ldg(p.label + img_px + (int64_t)py * W + px);
+        if (has_lay && p.need_grad) nvalid_pre = __ldcg(&p.hdr->n_valid);
+    }
+
     // ---------------- phase 0a: base grid of the region's rows / columns ----------------
     if (WARP) {
         if (tid < kRW) sm.bx[tid] = base_coord(tx0 - kHalo + tid, cc.Wm1);
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         }
 
         if (has_lay) {
-            const int64_t lab = __ldg(p.label + img_px + o);
+            const int64_t lab = lab_pre;
             const bool lab_ok = lab >= 0 && lab < K;
             if (!lab_ok && lab != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
             const int il = lab_ok ? (int)lab : 0;
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
             }
             if (lab_ok) s_ce += fmaf(lg2_approx(se), 0.6931471805599453f, m) - zl;
             if (p.need_grad) {
-                const float nv = (float)p.hdr->n_valid;
+                const float nv = (float)nvalid_pre;
                 const float cce = lab_ok ? p.w_ce_over_scale / nv : 0.0f;
                 const float inv = cce / se;
                 // d/dz_k = cce * (softmax_k - [k == label]); the one-hot part is applied to the label

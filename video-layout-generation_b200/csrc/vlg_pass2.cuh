@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     const int ty0 = blockIdx.y * kTH, tx0 = blockIdx.x * kTW;
     const int64_t img_px = (int64_t)n * H * W;
 
+    const uint32_t tile_far = p.far_acc ? __ldg(p.tile_flags + bt) : 0u;   // consumed at the very end: issue early
     const int r = near_radius(p, n, blockIdx.y, blockIdx.x);
     const int qw = kTW + 2 * r, qh = kTH + 2 * r;
     const bool want_rgb = p.d_src_rgb != nullptr && p.d_out_rgb != nullptr;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
         }
     }
     const int64_t so = img_px + (int64_t)sy * W + sx;
-    if (live && p.far_acc && p.tile_flags[bt]) {
+    if (live && tile_far) {
         const double inv = 1.0 / far_scale(p.hdr, p.HW);
         const long long *fa = p.far_acc + so * (3 + K);
 #pragma unroll
