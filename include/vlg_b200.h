@@ -125,6 +125,12 @@ int vlg_warp_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src
 int vlg_warp_fwd_labels(const vlg_problem_t *prob, const void *src_rgb, const int64_t *src_label,
                         const float *coords, void *out_rgb, int64_t *out_label, void *stream);
 
+/* Layout visualisation (src/trainer.py:416-427 vis_seg_mask, src/val.py:178): colour = lut[class]/255.
+ *   layout [N,H,W,K] (argmax taken here, first max on ties)  XOR  label [N,H,W] i64
+ *   lut_rgb: K*3 bytes on the device;  out_rgb [N,H,W,3];  out_label nullable (argmax output) */
+int vlg_colorize(const vlg_problem_t *prob, const void *layout, const int64_t *label,
+                 const uint8_t *lut_rgb, void *out_rgb, int64_t *out_label, void *stream);
+
 /* Pass 1 of the fused op: warp + all loss terms + d(loss)/d(warped) + d(loss)/d(coords) in one
  * kernel.  Gradients are for an upstream grad of 1.0 (see vlg_scale_grads).
  *   tgt_rgb [N,H,W,3], tgt_label [N,H,W] i64

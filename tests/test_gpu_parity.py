@@ -411,3 +411,18 @@ def test_rollout_five_steps_matches_dense_feedback():
         lay = torch.zeros_like(lay).scatter_(1, arg[:, None], 1.0)     # argmax -> one-hot feedback
         assert torch.equal(labs[t], arg), t
         assert torch.equal(imgs[t], img), t
+
+
+def test_colorize_matches_vis_seg_mask():
+    """src/trainer.py:416-427: rgb = color_map[argmax(seg)] / 255, as NCHW float."""
+    K = 20
+    g = torch.Generator().manual_seed(5)
+    seg = torch.randn(2, K, 33, 47, generator=g)
+    seg[0, 3, 0, 0] = seg[0, 7, 0, 0] = 9.0            # tie -> first index
+    pal = torch.tensor(vlg_b200.CITYSCAPES_PALETTE)
+    want = pal[torch.argmax(seg, 1)].permute(0, 3, 1, 2).contiguous().float() / 255
+    got = vlg_b200.colorize(_cl(seg), K, argmax=True)
+    assert torch.equal(got.cpu().contiguous(), want)
+    ids = torch.argmax(seg, 1)
+    got2 = vlg_b200.colorize(ids.to(DEV), K)
+    assert torch.equal(got2.cpu().contiguous(), want)

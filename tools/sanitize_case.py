@@ -1,0 +1,32 @@
+"""Small end-to-end case for compute-sanitizer (one tool per gpurun call):
+    compute-sanitizer --tool memcheck python tools/sanitize_case.py
+Covers pass 1 (staged + global fallback), pass 2 near + far paths, pixel-loss mode, forward warps."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vlg_b200
+
+dev = "cuda"
+torch.manual_seed(0)
+for (N, H, W, sigma, far) in ((1, 37, 70, 1.5, 0.0), (2, 24, 45, 6.0, 0.05)):
+    K = 20
+    cl = lambda t: t.to(dev).contiguous(memory_format=torch.channels_last)
+    a = cl(torch.randn(N, 3, H, W)).requires_grad_(True)
+    b = cl(torch.randn(N, K, H, W)).requires_grad_(True)
+    f = torch.randn(N, H, W, 2) * sigma
+    if far:
+        m = torch.rand(N, H, W, 1) < far
+        f = torch.where(m, (torch.rand(N, H, W, 2) - 0.5) * 2 * W, f)
+    f = f.to(dev).requires_grad_(True)
+    t = cl(torch.randn(N, 3, H, W))
+    lab = torch.randint(0, K, (N, H, W), device=dev)
+    for pad in ("border", "zeros"):
+        total, vec, arg = vlg_b200.warp_loss(a, b, f, t, lab, vlg_b200.WarpLossConfig(w_tv=0.5, padding_mode=pad, want_argmax=True))
+        total.backward()
+        vlg_b200.warp(a.detach(), b.detach(), f.detach(), padding_mode=pad)
+        vlg_b200.warp_labels(a.detach(), lab, f.detach(), padding_mode=pad)
+    img = cl(torch.randn(N, 3, H, W)).requires_grad_(True)
+    seg = cl(torch.randn(N, K, H, W)).requires_grad_(True)
+    vlg_b200.PixelLosses()(img, t, seg, lab).backward()
+torch.cuda.synchronize()
+print("sanitize case done", float(total))

@@ -183,6 +183,38 @@ __global__ void __launch_bounds__(256) warp_fwd_labels_kernel(CoordCfg cc, int64
     }
 }
 
+// Visualisation of a layout (src/trainer.py:416-427 vis_seg_mask, src/val.py:178): optional argmax
+// over K channels, then a K-entry colour LUT, output rgb = lut / 255 as NHWC T.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) colorize_kernel(int64_t P, const T *__restrict__ layout, const int64_t *__restrict__ label,
+                                                       const uint8_t *__restrict__ lut, T *out_rgb, int64_t *out_label,
+                                                       WsHeader *hdr_or_null) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int64_t l;
+    if (layout) {
+        float z[K];
+        load_px<T, K>(layout + i * K, z);
+        float m = z[0];
+        int best = 0;
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+            if (z[k] > m) { m = z[k]; best = k; }   // first maximal index
+        l = best;
+        if (out_label) out_label[i] = l;
+    } else {
+        l = __ldg(label + i);
+    }
+    float rgb[3] = {0.f, 0.f, 0.f};
+    if (l >= 0 && l < K) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb[c] = __fdiv_rn((float)__ldg(lut + l * 3 + c), 255.0f);
+    } else if (hdr_or_null) {
+        atomicOr(&hdr_or_null->status, VLG_STATUS_BAD_LABEL);
+    }
+    store_px<T, 3>(out_rgb + i * 3, rgb);
+}
+
 // forward-only warp (validation / rollout): one thread per output pixel
 template <typename T, int K>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, int64_t HW, const T *__restrict__ src_rgb,
@@ -331,6 +363,14 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     return dispatch_pass1(prob, warp, pp, L.n_blocks, st);
 }
 
+template <typename T, int K>
+static int launch_colorize(int64_t P, const void *layout, const int64_t *label, const uint8_t *lut, void *out_rgb,
+                           int64_t *out_label, cudaStream_t st) {
+    colorize_kernel<T, K><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, (const T *)layout, label, lut, (T *)out_rgb,
+                                                                      out_label, nullptr);
+    return check_launch("colorize_kernel");
+}
+
 // ------------------------------------------------------------------ exported C ABI
 extern "C" {
 
@@ -376,6 +416,23 @@ int vlg_warp_fwd_labels(const vlg_problem_t *prob, const void *src_rgb, const in
                                                                       src_label, (const float2 *)coords,
                                                                       (__nv_bfloat16 *)out_rgb, out_label);
     return check_launch("warp_fwd_labels_kernel");
+}
+
+int vlg_colorize(const vlg_problem_t *prob, const void *layout, const int64_t *label, const uint8_t *lut_rgb,
+                 void *out_rgb, int64_t *out_label, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if ((layout == nullptr) == (label == nullptr)) return fail(VLG_ERR_ARG, "give exactly one of layout / label");
+    if (!lut_rgb || !out_rgb) return fail(VLG_ERR_ARG, "lut_rgb and out_rgb are required");
+    const int64_t P = prob->N * prob->H * prob->W;
+    cudaStream_t st = (cudaStream_t)stream;
+#define X(k)                                                                                              \
+    if (prob->K == k)                                                                                     \
+        return prob->dtype == VLG_F32 ? launch_colorize<float, k>(P, layout, label, lut_rgb, out_rgb, out_label, st) \
+                                      : launch_colorize<__nv_bfloat16, k>(P, layout, label, lut_rgb, out_rgb, out_label, st);
+    VLG_FOR_EACH_K(X)
+#undef X
+    return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
 }
 
 static int warp_loss_pass1(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,

@@ -157,6 +157,40 @@ def warp_labels(src_rgb: Optional[torch.Tensor], src_label: torch.Tensor, coords
     return out_rgb, out_lab
 
 
+# Cityscapes train-id palette (19 classes + "None"), the table `vis_seg_mask` indexes at
+# src/trainer.py:31-52,416-427
+CITYSCAPES_PALETTE = (
+    (128, 64, 128), (244, 35, 232), (70, 70, 70), (102, 102, 156), (190, 153, 153), (153, 153, 153),
+    (250, 170, 30), (220, 220, 0), (107, 142, 35), (152, 251, 152), (70, 130, 180), (220, 20, 60),
+    (255, 0, 0), (0, 0, 142), (0, 0, 70), (0, 60, 100), (0, 80, 100), (0, 0, 230), (119, 11, 32), (0, 0, 0))
+
+
+@torch.no_grad()
+def colorize(seg: torch.Tensor, n_classes: int = 20, argmax: bool = False, palette=CITYSCAPES_PALETTE,
+             dtype=torch.float32):
+    """`Trainer.vis_seg_mask(seg, n_classes, argmax)` (src/trainer.py:416-427): layout -> RGB in [0,1].
+    seg: [N,K,H,W] scores (argmax=True) or int64 [N,H,W] class ids.  Returns [N,3,H,W] (channels_last)."""
+    lib = _cabi.load()
+    _require_cuda(seg)
+    if len(palette) != n_classes:
+        raise VlgError("palette length must equal n_classes")
+    lut = torch.tensor(palette, dtype=torch.uint8, device=seg.device).contiguous()
+    if argmax:
+        N, K, H, W = seg.shape
+        if K != n_classes:
+            raise VlgError("seg has a different number of channels than n_classes")
+        lay, lab, dt = to_nhwc(seg), None, seg.dtype
+    else:
+        if seg.dtype != torch.int64 or seg.dim() != 3:
+            raise VlgError("class-id input must be int64 [N,H,W]")
+        N, H, W = seg.shape
+        lay, lab, dt = None, seg.contiguous(), dtype
+    prob = _problem(N, H, W, n_classes, dt, WarpLossConfig())
+    out = empty_nhwc((N, 3, H, W), dt, seg.device)
+    check(lib.vlg_colorize(C.byref(prob), _ptr(lay), _ptr(lab), _ptr(lut), _ptr(out), None, _stream()))
+    return out
+
+
 @torch.no_grad()
 def rollout(img: torch.Tensor, label: torch.Tensor, flow_fn, steps: int = 5, *, padding_mode: str = "border"):
     """Autoregressive rollout (shape of src/trainer.py:453-476, which runs 8 steps and feeds the
