@@ -58,6 +58,10 @@ extern "C" {
 #define VLG_TERM_TV 16u
 #define VLG_TERM_ALL 31u
 
+/* ce_norm */
+#define VLG_CE_NORM_TORCH 0u /* sum_p w[l_p] nll_p / sum_p w[l_p]   (torch 'mean'; w == 1 without weights) */
+#define VLG_CE_NORM_COUNT 1u /* sum_p w[l_p] nll_p / #{labels != ignore_index}    (src/models/simple.py:56-59) */
+
 /* error codes (negative) */
 #define VLG_OK 0
 #define VLG_ERR_ARG (-1)
@@ -93,10 +97,14 @@ typedef struct vlg_problem {
     int64_t ignore_index; /* nn.CrossEntropyLoss default -100 (src/trainer.py:124)                 */
     float w_l1, w_gd, w_ssim, w_ce, w_tv; /* 40, 20, 20, 10 (src/trainer.py:248-250) + TV weight  */
     uint32_t term_mask;   /* VLG_TERM_* bits to evaluate; 0 = all.  Skipped terms read as 0.       */
-    uint32_t reserved;
+    uint32_t ce_norm;     /* VLG_CE_NORM_*: divisor of the (weighted) cross-entropy sum                 */
     /* Divisors of the means.  0 = derive from N,H,W (single GPU).  Data-parallel ranks pass the
      * GLOBAL batch here so that per-rank loss vectors and gradients simply add. */
     int64_t global_N;
+    /* Optional per-class CE weights (device pointer, K floats; NULL = unweighted).  The reference's
+     * class-weighted variant: F.cross_entropy(weight=w, reduction='sum') / n_known, src/models/simple.py:56-59
+     * (= VLG_CE_NORM_COUNT); nn.CrossEntropyLoss(weight=w) semantics are VLG_CE_NORM_TORCH. */
+    const float *ce_class_weight;
 } vlg_problem_t;
 
 int vlg_version(void);

@@ -41,7 +41,7 @@ int main(void){
   printf("%zu", sizeof(vlg_problem_t));
 #define O(f) printf(" %zu", offsetof(vlg_problem_t, f));
   O(N) O(H) O(W) O(K) O(dtype) O(padding) O(coord_mode) O(flags) O(ignore_index)
-  O(w_l1) O(w_gd) O(w_ssim) O(w_ce) O(w_tv) O(term_mask) O(reserved) O(global_N)
+  O(w_l1) O(w_gd) O(w_ssim) O(w_ce) O(w_tv) O(term_mask) O(ce_norm) O(global_N) O(ce_class_weight)
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -52,7 +52,7 @@ int main(void){
         vals = [int(v) for v in subprocess.check_output([exe]).split()]
     P = _cabi.Problem
     names = ["N", "H", "W", "K", "dtype", "padding", "coord_mode", "flags", "ignore_index", "w_l1", "w_gd",
-             "w_ssim", "w_ce", "w_tv", "term_mask", "reserved", "global_N"]
+             "w_ssim", "w_ce", "w_tv", "term_mask", "ce_norm", "global_N", "ce_class_weight"]
     assert vals[0] == C.sizeof(P)
     assert vals[1:] == [getattr(P, n).offset for n in names]
 

@@ -426,3 +426,44 @@ def test_colorize_matches_vis_seg_mask():
     ids = torch.argmax(seg, 1)
     got2 = vlg_b200.colorize(ids.to(DEV), K)
     assert torch.equal(got2.cpu().contiguous(), want)
+
+
+# ------------------------------------------------------------------ loss variants
+def test_class_weighted_cross_entropy_variants():
+    """nn.CrossEntropyLoss(weight=w) (weighted mean) and the reference's class-weighted variant
+    F.cross_entropy(weight=w, reduction='sum') / n_known (src/models/simple.py:56-59), with ignored
+    labels; loss, gradient and bitwise run-to-run reproducibility of the weighted divisor."""
+    K = 20
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(2, K, 45, 67, generator=g)
+    label = torch.randint(0, K, (2, 45, 67), generator=g)
+    label[0, :5] = -100
+    w = torch.rand(K, generator=g) + 0.25
+    for reduction in ("mean", "sum_over_known"):
+        z = logits.clone().requires_grad_(True)
+        if reduction == "mean":
+            ref = torch.nn.functional.cross_entropy(z, label, weight=w, reduction="mean")
+        else:
+            ref = torch.nn.functional.cross_entropy(z, label, weight=w, reduction="sum") / (label != -100).sum()
+        ref.backward()
+        outs = []
+        for _ in range(3):
+            zz = _cl(logits).requires_grad_(True)
+            crit = vlg_b200.CrossEntropyLoss(weight=w, reduction=reduction).to(DEV)
+            loss = crit(input=zz, target=label.to(DEV))
+            loss.backward()
+            outs.append((loss.detach().clone(), zz.grad.clone()))
+        np.testing.assert_allclose(outs[0][0].item(), ref.item(), rtol=RTOL)
+        _assert_close_norm(_nchw(outs[0][1]), z.grad.numpy(), RTOL, "d_logits " + reduction)
+        for o in outs[1:]:
+            assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
+    # the fused warp op takes the same weights
+    d = _make_case(1, 40, 64, K, 1.5, seed=2, layout="soft")
+    b = _cl(d["src_layout"]).requires_grad_(True)
+    cfg = vlg_b200.WarpLossConfig(class_weight=w.to(DEV))
+    total, vec, _ = vlg_b200.warp_loss(_cl(d["src_rgb"]), b, d["flow"].to(DEV), _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV), cfg)
+    total.backward()
+    rb = d["src_layout"].clone().requires_grad_(True)
+    wl = TO.warp(rb, TO.flow_to_grid(d["flow"]))
+    ce = torch.nn.functional.cross_entropy(wl, d["tgt_label"], weight=w)
+    np.testing.assert_allclose(vec[_cabi.LOSS_CE].item(), ce.item(), rtol=RTOL)

@@ -12,6 +12,7 @@ COORD_FLOW, COORD_GRID = 0, 1
 FLAG_NO_FAR_PATH = 1
 TERM_L1, TERM_GD, TERM_SSIM, TERM_CE, TERM_TV, TERM_ALL = 1, 2, 4, 8, 16, 31
 STATUS_BAD_LABEL, STATUS_FAR_TAPS = 1, 2
+CE_NORM_TORCH, CE_NORM_COUNT = 0, 1
 NEAR_RADIUS = 3
 LOSS_L1, LOSS_GD, LOSS_SSIM, LOSS_CE, LOSS_TV, LOSS_TOTAL, LOSS_NVALID, LOSS_MAXDISP, LOSS_SLOTS = range(9)
 
@@ -30,8 +31,8 @@ class Problem(C.Structure):
         ("dtype", C.c_int32), ("padding", C.c_int32), ("coord_mode", C.c_int32), ("flags", C.c_uint32),
         ("ignore_index", C.c_int64),
         ("w_l1", C.c_float), ("w_gd", C.c_float), ("w_ssim", C.c_float), ("w_ce", C.c_float), ("w_tv", C.c_float),
-        ("term_mask", C.c_uint32), ("reserved", C.c_uint32),
-        ("global_N", C.c_int64),
+        ("term_mask", C.c_uint32), ("ce_norm", C.c_uint32),
+        ("global_N", C.c_int64), ("ce_class_weight", C.c_void_p),
     ]
 
 

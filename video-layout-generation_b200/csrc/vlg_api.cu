@@ -52,6 +52,8 @@ static int check_problem(const vlg_problem_t *p) {
     if (p->padding != VLG_PAD_ZEROS && p->padding != VLG_PAD_BORDER) return fail(VLG_ERR_ARG, "bad padding %d", p->padding);
     if (p->coord_mode != VLG_COORD_FLOW && p->coord_mode != VLG_COORD_GRID) return fail(VLG_ERR_ARG, "bad coord_mode %d", p->coord_mode);
     if (p->global_N != 0 && p->global_N < p->N) return fail(VLG_ERR_ARG, "global_N < N");
+    if (p->ce_norm != VLG_CE_NORM_TORCH && p->ce_norm != VLG_CE_NORM_COUNT) return fail(VLG_ERR_ARG, "bad ce_norm %u", p->ce_norm);
+    if (p->ce_class_weight && p->K > 32) return fail(VLG_ERR_UNSUPPORTED, "class weights need K <= 32");
     return VLG_OK;
 }
 
@@ -89,13 +91,27 @@ static CoordCfg make_cc(const vlg_problem_t *p) {
 }
 
 // ------------------------------------------------------------------ small kernels
-__global__ void count_valid_kernel(const int64_t *__restrict__ label, int64_t P, int64_t ignore_index, WsHeader *hdr) {
+// Counts the labels != ignore_index (CE divisor).  With class weights it also builds the per-class
+// histogram with INTEGER atomics, and the last CTA (ticket) derives sum_k w_k * hist_k in a fixed
+// order: the weighted divisor is bitwise reproducible.
+__global__ void count_valid_kernel(const int64_t *__restrict__ label, int64_t P, int64_t ignore_index, int K,
+                                   const float *__restrict__ class_weight, WsHeader *hdr) {
+    __shared__ unsigned int s[32];
+    __shared__ unsigned int sh[32];
+    __shared__ int s_last;
+    if (threadIdx.x < 32) sh[threadIdx.x] = 0u;
+    __syncthreads();
     unsigned int cnt = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride)
-        cnt += __ldg(label + i) != ignore_index;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+        const int64_t l = __ldg(label + i);
+        cnt += l != ignore_index;
+        if (class_weight && l >= 0 && l < K) {
+            const unsigned peers = __match_any_sync(__activemask(), (int)l);   // one smem atomic per distinct class
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[l], (unsigned)__popc(peers));
+        }
+    }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    __shared__ unsigned int s[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) s[wid] = cnt;
     __syncthreads();
@@ -103,6 +119,19 @@ __global__ void count_valid_kernel(const int64_t *__restrict__ label, int64_t P,
         unsigned int v = lane < (blockDim.x >> 5) ? s[lane] : 0u;
         v = __reduce_add_sync(0xffffffffu, v);
         if (lane == 0 && v) atomicAdd(&hdr->n_valid, (unsigned long long)v);
+    }
+    if (class_weight) {
+        if (threadIdx.x < K && sh[threadIdx.x]) atomicAdd(&hdr->hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&hdr->count_done, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            __threadfence();
+            double d = 0.0;
+            for (int k = 0; k < K; ++k) d += (double)__ldg(class_weight + k) * (double)__ldcg(&hdr->hist[k]);
+            hdr->ce_denom = d;
+        }
     }
 }
 
@@ -124,6 +153,7 @@ static ReduceParams make_reduce_params(const vlg_problem_t *prob, const WsLayout
     rp.inv_tvw = 1.0 / (Ng * H * (W - 1) * 2);
     rp.ce_scale = (double)prob->N / Ng;
     rp.w_l1 = prob->w_l1; rp.w_gd = prob->w_gd; rp.w_ssim = prob->w_ssim; rp.w_ce = prob->w_ce; rp.w_tv = prob->w_tv;
+    rp.weighted_denom = prob->ce_class_weight != nullptr && prob->ce_norm == VLG_CE_NORM_TORCH;
     rp.out = loss_out;   // NULL: pass 1 does not fuse the final reduction
     return rp;
 }
@@ -327,7 +357,8 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     const bool has_lay = src_layout && tgt_label;
     if (has_lay) {
         const int blocks = (int)((P + 256 * 8 - 1) / (256 * 8));
-        count_valid_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(tgt_label, P, prob->ignore_index, hdr);
+        count_valid_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(tgt_label, P, prob->ignore_index, (int)prob->K,
+                                                                     prob->ce_class_weight, hdr);
         int rc = check_launch("count_valid_kernel");
         if (rc) return rc;
     }
@@ -340,6 +371,8 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.tiles_y = (int)tiles_y(prob->H);
     pp.src_rgb = src_rgb; pp.src_layout = src_layout; pp.coords = coords;
     pp.tgt_rgb = tgt_rgb; pp.label = tgt_label; pp.ignore_index = prob->ignore_index;
+    pp.class_weight = prob->ce_class_weight;
+    pp.weighted_denom = prob->ce_class_weight != nullptr && prob->ce_norm == VLG_CE_NORM_TORCH;
     pp.c_l1 = (float)(prob->w_l1 / (Ng * 3 * H * W));
     pp.c_gd = (float)(prob->w_gd / (Ng * 3 * H * W));
     pp.c_ssim = (prob->H > 2 && prob->W > 2) ? (float)(prob->w_ssim / (2.0 * Ng * (H - 2) * (W - 2))) : 0.f;

@@ -24,9 +24,13 @@ struct WsHeader {
     unsigned long long n_valid;  // labels != ignore_index
     uint32_t blocks_done;   // pass-1 CTAs that have published their partial sums (last one reduces)
     uint32_t n_flagged;     // source tiles that receive far contributions (length of the flagged list)
-    uint32_t pad[24];
+    uint32_t count_done;    // label-count CTAs finished (the last one derives ce_denom)
+    uint32_t pad0;
+    double ce_denom;        // divisor of the weighted CE sum: sum_k w_k * hist_k (VLG_CE_NORM_TORCH with weights)
+    uint32_t pad[20];
+    unsigned long long hist[32];  // labels per class (only filled when class weights are given)
 };
-static_assert(sizeof(WsHeader) == 128, "header size");
+static_assert(sizeof(WsHeader) == 384, "header size");
 
 constexpr int kPartialSlots = 8;  // l1, gd, ssim, ce, tv_h, tv_w, n_valid(unused), spare
 
@@ -41,6 +45,7 @@ struct ReduceParams {
     double inv_tvh, inv_tvw;
     double ce_scale;        // N_local/N_global
     float w_l1, w_gd, w_ssim, w_ce, w_tv;
+    int weighted_denom;     // 1: CE divisor = hdr->ce_denom (class-weighted torch mean), 0: n_valid
     float *out;
 };
 
@@ -65,7 +70,8 @@ __device__ __forceinline__ void reduce_partials_block(const ReduceParams &p, dou
         const double nv = (double)__ldcg(&p.hdr->n_valid);
         const double l1 = s[0] * p.inv_numel_rgb, gd = s[256] * p.inv_numel_rgb;
         const double ssim = s[512] * p.inv_ssim;
-        const double ce = nv > 0 ? s[768] / nv * p.ce_scale : 0.0;
+        const double cd = p.weighted_denom ? __ldcg(&p.hdr->ce_denom) : nv;
+        const double ce = cd > 0 ? s[768] / cd * p.ce_scale : 0.0;
         const double tv = s[1024] * p.inv_tvh + s[1280] * p.inv_tvw;
         p.out[VLG_LOSS_L1] = (float)l1;
         p.out[VLG_LOSS_GD] = (float)gd;

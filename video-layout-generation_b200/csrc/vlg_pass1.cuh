@@ -35,6 +35,8 @@ struct Pass1Params {
     const void *tgt_rgb;
     const int64_t *label;
     int64_t ignore_index;
+    const float *class_weight;   // per-class CE weights (K floats) or NULL
+    int weighted_denom;          // 1: CE divisor = hdr->ce_denom, 0: number of valid labels
     // gradient scales (upstream grad 1.0), host-computed in double
     float c_l1, c_gd, c_ssim, c_tvh, c_tvw;
     float w_ce_over_scale;  // w_ce * (N_local/N_global); divided by n_valid on the device
@@ -180,11 +182,15 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
     // Loads whose consumers sit in phase 2 are issued now, so that their (L2/DRAM) latency is
     // hidden behind phases 0-1 instead of stalling the longest phase.
     int64_t lab_pre = 0;
-    unsigned long long nvalid_pre = 0;
+    float denom_pre = 1.0f, wl_pre = 1.0f;
     {
         const int py = ty0 + tid / kTW, px = tx0 + (tid & (kTW - 1));
-        if (has_lay && py < H && px < W) lab_pre = __ldg(p.label + img_px + (int64_t)py * W + px);
-        if (has_lay && p.need_grad) nvalid_pre = __ldcg(&p.hdr->n_valid);
+        if (has_lay && py < H && px < W) {
+            lab_pre = __ldg(p.label + img_px + (int64_t)py * W + px);
+            if (p.class_weight && lab_pre >= 0 && lab_pre < K) wl_pre = __ldg(p.class_weight + lab_pre);
+        }
+        if (has_lay && p.need_grad)
+            denom_pre = p.weighted_denom ? (float)__ldcg(&p.hdr->ce_denom) : (float)__ldcg(&p.hdr->n_valid);
     }
 
     // ---------------- phase 0a: base grid of the region's rows / columns ----------------
@@ -505,10 +511,9 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                 z[k] = ex2_approx(fmaf(z[k], L2E, -ml2));
                 se += z[k];
             }
-            if (lab_ok) s_ce += fmaf(lg2_approx(se), 0.6931471805599453f, m) - zl;
+            if (lab_ok) s_ce += wl_pre * (fmaf(lg2_approx(se), 0.6931471805599453f, m) - zl);
             if (p.need_grad) {
-                const float nv = (float)nvalid_pre;
-                const float cce = lab_ok ? p.w_ce_over_scale / nv : 0.0f;
+                const float cce = lab_ok ? p.w_ce_over_scale * wl_pre / denom_pre : 0.0f;
                 const float inv = cce / se;
                 // d/dz_k = cce * (softmax_k - [k == label]); the one-hot part is applied to the label
                 // channel alone (a scalar fix-up store / a rank-1 term of the coordinate gradient)

@@ -79,16 +79,24 @@ class CrossEntropyLoss(_Criterion):
     """nn.CrossEntropyLoss(reduction='mean') as constructed at src/trainer.py:124."""
     _mask = _cabi.TERM_CE
 
-    def __init__(self, ignore_index: int = -100, reduction: str = "mean"):
+    def __init__(self, weight: Optional[torch.Tensor] = None, ignore_index: int = -100, reduction: str = "mean"):
+        """reduction='mean' is nn.CrossEntropyLoss (weighted mean when `weight` is given);
+        reduction='sum_over_known' is the reference's class-weighted variant
+        `F.cross_entropy(weight=w, reduction='sum') / n_known` (src/models/simple.py:56-59)."""
         super().__init__()
-        if reduction != "mean":
-            raise ValueError("only reduction='mean' (the reference's setting) is implemented")
+        if reduction not in ("mean", "sum_over_known"):
+            raise ValueError("reduction must be 'mean' or 'sum_over_known'")
         self.ignore_index = ignore_index
+        self.reduction = reduction
+        self.register_buffer("weight", None if weight is None else weight.detach().float().contiguous())
 
     def forward(self, input, target):
         cfg = self._cfg()
         cfg.w_ce = 1.0
         cfg.ignore_index = self.ignore_index
+        cfg.ce_norm = "count" if self.reduction == "sum_over_known" else "torch"
+        if self.weight is not None:
+            cfg.class_weight = self.weight.to(input.device)
         return pixel_losses(None, None, input, target, cfg)[0]
 
 

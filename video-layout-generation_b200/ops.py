@@ -39,6 +39,8 @@ class WarpLossConfig:
     global_batch: int = 0                 # data-parallel: divisor batch (0 = local batch)
     assume_near: bool = False             # caller asserts |flow| < NEAR_RADIUS: skip far-path launches
     term_mask: int = 0                    # 0 = all terms
+    class_weight: Optional[torch.Tensor] = None   # per-class CE weights (K floats on the device)
+    ce_norm: str = "torch"                # 'torch' (weighted mean) | 'count' (sum / n_known, src/models/simple.py:56-59)
     want_argmax: bool = False
 
 
@@ -86,6 +88,15 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _class_weight_ptr(cfg: "WarpLossConfig", K: int):
+    w = cfg.class_weight
+    if w is None:
+        return None
+    if not w.is_cuda or w.dtype != torch.float32 or w.numel() != K or not w.is_contiguous():
+        raise VlgError(f"class_weight must be a contiguous float32 CUDA tensor of {K} elements")
+    return w.data_ptr()
+
+
 def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
     if dtype not in _DTYPES:
         raise VlgError(f"unsupported activation dtype {dtype}; use float32 or bfloat16")
@@ -93,8 +104,9 @@ def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
     return Problem(N=N, H=H, W=W, K=K, dtype=_DTYPES[dtype], padding=_PADDING[cfg.padding_mode],
                    coord_mode=_cabi.COORD_GRID if cfg.coords_are_grid else _cabi.COORD_FLOW, flags=flags,
                    ignore_index=cfg.ignore_index, w_l1=cfg.w_l1, w_gd=cfg.w_gd, w_ssim=cfg.w_ssim,
-                   w_ce=cfg.w_ce, w_tv=cfg.w_tv, term_mask=cfg.term_mask, reserved=0,
-                   global_N=cfg.global_batch)
+                   w_ce=cfg.w_ce, w_tv=cfg.w_tv, term_mask=cfg.term_mask,
+                   ce_norm=_cabi.CE_NORM_COUNT if cfg.ce_norm == "count" else _cabi.CE_NORM_TORCH,
+                   global_N=cfg.global_batch, ce_class_weight=_class_weight_ptr(cfg, K))
 
 
 def _workspace(prob: Problem, with_src: bool, device) -> torch.Tensor:
