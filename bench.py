@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-eager", action="store_true", help="skip timing the torch CUDA eager incumbent")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step (iters/s) measurement")
     ap.add_argument("--flow-grad-only", action="store_true", help="sources are data: no d_src (128 B/px variant)")
@@ -213,15 +214,23 @@ def main():
     sp = C.c_void_p(stream.cuda_stream)
     ptr = vops._ptr
 
+    def launch_fused(s, sp_):
+        vops.check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
+                                             ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(loss), ptr(d_c), ptr(d_a),
+                                             ptr(d_b), None, ptr(ws), ws.numel(), sp_))
+
+    graphs = None
+    launches_per_step = None
+
     def step(i, evs=None):
         """One pass of the hot path.  The timed region uses the fused entry point (the last pass-1
         CTA reduces the loss vector); with `evs` the same work is issued piecewise so that CUDA
         events can bracket each kernel."""
         s = sets[i & 1]
-        if evs is None:
-            vops.check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
-                                                 ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(loss), ptr(d_c), ptr(d_a),
-                                                 ptr(d_b), None, ptr(ws), ws.numel(), sp))
+        if evs is None and graphs is not None:
+            graphs[i & 1].replay()                  # the same launches, captured once per input set
+        elif evs is None:
+            launch_fused(s, sp)
         else:
             vops.check(lib.vlg_warp_loss_bwd_out(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
                                                  ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(d_c), None, int(with_src),
@@ -243,6 +252,24 @@ def main():
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
+    # CUDA graph of the step's launches (memset + count + pass 1 + far path + pass 2), one per input set
+    if not args.no_graph:
+        try:
+            n_before = vlg_b200.launch_count()
+            gs = []
+            for k in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    launch_fused(sets[k], C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                gs.append(g)
+            launches_per_step = (vlg_b200.launch_count() - n_before) // 2
+            graphs = gs
+            for i in range(4):
+                step(i)
+            barrier()
+        except Exception as exc:   # capture unsupported: plain launches
+            print(f"[bench] CUDA graph capture failed ({exc}); using plain launches", file=sys.stderr)
+            graphs = None
 
     # ---- timed region 1: device-resident throughput (`value`) ----
     sampler = ClockSampler(local_rank)
@@ -257,6 +284,8 @@ def main():
     e1.record(stream)
     barrier()
     launches = vlg_b200.launch_count() - n0
+    if graphs is not None:
+        launches = launches_per_step * args.steps   # replayed from the graph: the host counter does not move
     ms_total = e0.elapsed_time(e1)
     t_step = torch.tensor([ms_total / args.steps], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -366,7 +395,7 @@ def main():
                                + ("" if with_src else " (flow-grad only)"),
                    "per_gpu_pixels": P, "grads": "flow,src_rgb,src_layout" if with_src else "flow",
                    "l2_policy": "inputs (%.0f MB/step) exceed the 126 MB L2; two input sets alternate" % (P * 120 / 1e6),
-                   "parallelism": f"dp{world}"},
+                   "parallelism": f"dp{world}", "launch": "cuda graph replay" if graphs is not None else "direct launches"},
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": P * dom_bytes,
