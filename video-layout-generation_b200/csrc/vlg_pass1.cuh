@@ -204,6 +204,67 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
     // ---------------- phase 0b: coordinates + rgb over the tile + halo ----------------
     {
         int bx0 = 1 << 30, by0 = 1 << 30, bx1 = -(1 << 30), by1 = -(1 << 30);
+        constexpr int kIt = (kRN + kThreads - 1) / kThreads;
+        if (WARP && has_rgb) {
+            // Branch-free, software-pipelined form of the generic loop below: every address is clamped
+            // into the image so that all loads are unconditional and the loads of BOTH region pixels
+            // of a thread are in flight together (coords -> 12 tap channels + 3 target channels);
+            // out-of-image taps are zeroed by a select, exactly like the predicated gather.
+            bool inside[kIt];
+            int64_t oc[kIt];
+            int rxs[kIt], rys[kIt];
+            float2 fl[kIt];
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) {
+                const int q = min(tid + it * kThreads, kRN - 1);
+                const int ry = q / kRW, rx = q - ry * kRW;
+                const int y = ty0 - kHalo + ry, x = tx0 - kHalo + rx;
+                inside[it] = tid + it * kThreads < kRN && y >= 0 && y < H && x >= 0 && x < W;
+                oc[it] = (int64_t)min(max(y, 0), H - 1) * W + min(max(x, 0), W - 1);
+                rxs[it] = rx; rys[it] = ry;
+                fl[it] = __ldg(coords + oc[it]);
+            }
+            Taps tp[kIt];
+            float v[kIt][4][3], tb[kIt][3];
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) {
+                float mx, my;
+                const float2 xy = source_xy(cc, fl[it], sm.bx[rxs[it]], sm.by[rys[it]], mx, my);
+                tp[it] = taps_from_xy(cc, xy, mx, my);
+                const bool own = rys[it] >= kHalo && rys[it] < kHalo + kTH && rxs[it] >= kHalo && rxs[it] < kHalo + kTW;
+                if (own && has_lay && inside[it]) {
+                    bx0 = min(bx0, tp[it].x0); bx1 = max(bx1, tp[it].x0);
+                    by0 = min(by0, tp[it].y0); by1 = max(by1, tp[it].y0);
+                }
+                const int x0c = min(max(tp[it].x0, 0), W - 1), x1c = min(max(tp[it].x0 + 1, 0), W - 1);
+                const int y0c = min(max(tp[it].y0, 0), H - 1), y1c = min(max(tp[it].y0 + 1, 0), H - 1);
+                load_px<T, 3>(src_rgb + ((int64_t)y0c * W + x0c) * 3, v[it][0]);
+                load_px<T, 3>(src_rgb + ((int64_t)y0c * W + x1c) * 3, v[it][1]);
+                load_px<T, 3>(src_rgb + ((int64_t)y1c * W + x0c) * 3, v[it][2]);
+                load_px<T, 3>(src_rgb + ((int64_t)y1c * W + x1c) * 3, v[it][3]);
+                load_px<T, 3>(tgt_rgb + oc[it] * 3, tb[it]);
+            }
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) {
+                const Taps &t = tp[it];
+                const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+                const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+                const int q = tid + it * kThreads;
+                if (q < kRN) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float acc = __fmul_rn(yin0 && xin0 ? v[it][0][c] : 0.0f, t.nw);
+                        acc = __fmaf_rn(yin0 && xin1 ? v[it][1][c] : 0.0f, t.ne, acc);
+                        acc = __fmaf_rn(yin1 && xin0 ? v[it][2][c] : 0.0f, t.sw, acc);
+                        acc = __fmaf_rn(yin1 && xin1 ? v[it][3][c] : 0.0f, t.se, acc);
+                        sm.ab[c][q] = inside[it] ? make_float2(acc, tb[it][c]) : make_float2(0.f, 0.f);
+                    }
+#if VLG_P1_FLOW_IN_SMEM
+                    sm.flow[q] = inside[it] ? fl[it] : make_float2(0.f, 0.f);
+#endif
+                }
+            }
+        } else
 #pragma unroll
         for (int it = 0; it < (kRN + kThreads - 1) / kThreads; ++it) {
             const int q = tid + it * kThreads;
