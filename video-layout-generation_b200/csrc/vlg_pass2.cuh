@@ -40,13 +40,17 @@ struct Pass2Params {
 // inside the 3x3 neighbourhood of tiles (kRMax < kTH); far pixels (disp >= kRMax) are excluded from
 // the per-tile maxima and travel through the fixed-point path instead.
 __device__ __forceinline__ int near_radius(const Pass2Params &p, int n, int tyi, int txi) {
+    // nine independent loads; neighbours outside the image are clamped onto an existing tile so that
+    // no load is predicated (the maximum is unaffected) and all nine are in flight together
+    float v[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const int yy = min(max(tyi + j / 3 - 1, 0), p.tiles_y - 1), xx = min(max(txi + j % 3 - 1, 0), p.tiles_x - 1);
+        v[j] = __ldg(p.tile_disp + ((int64_t)n * p.tiles_y + yy) * p.tiles_x + xx);
+    }
     float m = 0.f;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int yy = tyi + dy, xx = txi + dx;
-            if (yy >= 0 && yy < p.tiles_y && xx >= 0 && xx < p.tiles_x)
-                m = fmaxf(m, __ldg(p.tile_disp + ((int64_t)n * p.tiles_y + yy) * p.tiles_x + xx));
-        }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) m = fmaxf(m, v[j]);
     return min(kRMax, (int)floorf(m) + 1);
 }
 
@@ -108,34 +112,45 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
             for (int i = lane; i < (xb - xa) * 3; i += 32) s_rgb[q0 * 3 + i] = __ldg(p.d_out_rgb + g0 * 3 + i);
     }
     // ---- sampling coordinates of the candidate output pixels ----
+    // flat index over the region, addresses clamped into the image: the (up to three) coords loads of
+    // a thread are unconditional and issued before the barrier, together with the cp.async above
+    const float2 *coords = reinterpret_cast<const float2 *>(p.coords) + img_px;
+    const int qn = qw * qh;
+    const float inv_qw = 1.0f / (float)qw;
+    constexpr int kQIt = (kQN + kThreads - 1) / kThreads;
+    float2 cf[kQIt];
+    int cry[kQIt], crx[kQIt];
+#pragma unroll
+    for (int it = 0; it < kQIt; ++it) {
+        const int q = min(tid + it * kThreads, qn - 1);
+        const int ry = (int)(((float)q + 0.5f) * inv_qw), rx = q - ry * qw;   // exact for these small integers
+        cry[it] = ry; crx[it] = rx;
+        const int y = min(max(ty0 - r + ry, 0), H - 1), x = min(max(tx0 - r + rx, 0), W - 1);
+        cf[it] = __ldg(coords + (int64_t)y * W + x);
+    }
     if (tid < qw) s_bx[tid] = base_coord(tx0 - r + tid, cc.Wm1);
     else if (tid >= 64 && tid < 64 + qh) s_by[tid - 64] = base_coord(ty0 - r + tid - 64, cc.Hm1);
     __syncthreads();
     // Each candidate output pixel is reduced to a packed integer cell code (x0 | y0 << 16, relative
     // to the tile, biased by 8) plus its two fractional weights, so that the per-candidate test in
     // the gather below is three integer instructions.
-    const float2 *coords = reinterpret_cast<const float2 *>(p.coords) + img_px;
     uint32_t *s_code = reinterpret_cast<uint32_t *>(s_rgb + (size_t)kQN * 3);   // [kQN]
-    for (int ry = wid; ry < qh; ry += kThreads / 32) {
-        const int y = ty0 - r + ry;
-        for (int rx = lane; rx < qw; rx += 32) {
-            const int x = tx0 - r + rx;
-            uint32_t code = 0xFFFFFFFFu;   // never matches
-            float2 frac = make_float2(0.f, 0.f);
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                float mx, my;
-                const float2 s = source_xy(cc, __ldg(coords + (int64_t)y * W + x), s_bx[rx], s_by[ry], mx, my);
-                const float fx0 = floorf(s.x), fy0 = floorf(s.y);
-                const bool dead = fx0 < -1.0f || fx0 >= (float)W || fy0 < -1.0f || fy0 >= (float)H;  // no tap inside
-                const bool far = fmaxf(fabsf(s.x - (float)x), fabsf(s.y - (float)y)) >= (float)kRMax;
-                if (!far && !dead) {
-                    // near => |x0 - x| <= kRMax, so the biased fields stay within [0, 2^15)
-                    code = (uint32_t)((int)fx0 - tx0 + 8) | ((uint32_t)((int)fy0 - ty0 + 8) << 16);
-                    frac = make_float2(__fsub_rn(s.x, fx0), __fsub_rn(s.y, fy0));
-                }
-            }
-            s_code[ry * qw + rx] = code;
-            s_xy[ry * qw + rx] = frac;
+#pragma unroll
+    for (int it = 0; it < kQIt; ++it) {
+        const int q = tid + it * kThreads;
+        if (q < qn) {
+            const int ry = cry[it], rx = crx[it];
+            const int y = ty0 - r + ry, x = tx0 - r + rx;
+            float mx, my;
+            const float2 sxy = source_xy(cc, cf[it], s_bx[rx], s_by[ry], mx, my);
+            const float fx0 = floorf(sxy.x), fy0 = floorf(sxy.y);
+            const bool in_img = y >= 0 && y < H && x >= 0 && x < W;
+            const bool dead = fx0 < -1.0f || fx0 >= (float)W || fy0 < -1.0f || fy0 >= (float)H;  // no tap inside
+            const bool far = fmaxf(fabsf(sxy.x - (float)x), fabsf(sxy.y - (float)y)) >= (float)kRMax;
+            const bool ok = in_img && !far && !dead;
+            // near => |x0 - x| <= kRMax, so the biased fields stay within [0, 2^15); 0xFFFFFFFF never matches
+            s_code[q] = ok ? ((uint32_t)((int)fx0 - tx0 + 8) | ((uint32_t)((int)fy0 - ty0 + 8) << 16)) : 0xFFFFFFFFu;
+            s_xy[q] = ok ? make_float2(__fsub_rn(sxy.x, fx0), __fsub_rn(sxy.y, fy0)) : make_float2(0.f, 0.f);
         }
     }
     cp_async_commit_wait_all();
