@@ -95,6 +95,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
@@ -514,7 +518,28 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
             }
             if (p.need_grad) {
                 if (WARP) {
-                    coord_grad_px<T, 3>(src_rgb, cc, t, dr, gix, giy);
+                    {   // branch-free form of coord_grad_px: clamped addresses, all 12 loads in flight together
+                        const int x0c = min(max(t.x0, 0), W - 1), x1c = min(max(t.x0 + 1, 0), W - 1);
+                        const int y0c = min(max(t.y0, 0), H - 1), y1c = min(max(t.y0 + 1, 0), H - 1);
+                        float tv[4][3];
+                        load_px<T, 3>(src_rgb + ((int64_t)y0c * W + x0c) * 3, tv[0]);
+                        load_px<T, 3>(src_rgb + ((int64_t)y0c * W + x1c) * 3, tv[1]);
+                        load_px<T, 3>(src_rgb + ((int64_t)y1c * W + x0c) * 3, tv[2]);
+                        load_px<T, 3>(src_rgb + ((int64_t)y1c * W + x1c) * 3, tv[3]);
+                        const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+                        const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+                        const bool tin[4] = {yin0 && xin0, yin0 && xin1, yin1 && xin0, yin1 && xin1};
+                        float dt4[4];
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float s3 = fmaf(dr[2], tv[k4][2], fmaf(dr[1], tv[k4][1], dr[0] * tv[k4][0]));
+                            dt4[k4] = tin[k4] ? s3 : 0.0f;
+                        }
+                        const float wx1 = t.ix - t.fx0, wx0 = (t.fx0 + 1.0f) - t.ix;
+                        const float wy1 = t.iy - t.fy0, wy0 = (t.fy0 + 1.0f) - t.iy;
+                        gix += (dt4[1] - dt4[0]) * wy0 + (dt4[3] - dt4[2]) * wy1;
+                        giy += (dt4[2] - dt4[0]) * wx0 + (dt4[3] - dt4[1]) * wx1;
+                    }
                     if (p.d_out_rgb) store_px<float, 3>(reinterpret_cast<float *>(p.d_out_rgb) + (img_px + o) * 3, dr);
                 } else if (p.d_out_rgb) {
                     store_px<T, 3>(reinterpret_cast<T *>(p.d_out_rgb) + (img_px + o) * 3, dr);

@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
                 for (int i = lane; i < (xb - xa) * K; i += 32) s_lay[(size_t)q0 * K + i] = __ldg(p.d_out_lay + g0 * K + i);
             }
         }
-        if (want_rgb)
-            for (int i = lane; i < (xb - xa) * 3; i += 32) s_rgb[q0 * 3 + i] = __ldg(p.d_out_rgb + g0 * 3 + i);
+        if (want_rgb)   // 12-byte pixels: 4-byte cp.async (no register round trip, completes with the group)
+            for (int i = lane; i < (xb - xa) * 3; i += 32) cp_async4(s_rgb + q0 * 3 + i, p.d_out_rgb + g0 * 3 + i);
     }
     // ---- sampling coordinates of the candidate output pixels ----
     // flat index over the region, addresses clamped into the image: the (up to three) coords loads of
