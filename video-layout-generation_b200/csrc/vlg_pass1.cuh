@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         if (tid < kRW) sm.bx[tid] = base_coord(tx0 - kHalo + tid, cc.Wm1);
         else if (tid >= 64 && tid < 64 + kRH) sm.by[tid - 64] = base_coord(ty0 - kHalo + tid - 64, cc.Hm1);
         if (tid == 128) { sm.bbox[0] = 1 << 30; sm.bbox[1] = 1 << 30; sm.bbox[2] = -(1 << 30); sm.bbox[3] = -(1 << 30); }
-        __syncthreads();
+        // (the barrier that publishes the table sits in phase 0b, after the coords loads were issued)
     }
 
     // ---------------- phase 0b: coordinates + rgb over the tile + halo ----------------
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                 rxs[it] = rx; rys[it] = ry;
                 fl[it] = __ldg(coords + oc[it]);
             }
+            __syncthreads();   // base-grid table ready; the coords loads above are already in flight
             Taps tp[kIt];
             float v[kIt][4][3], tb[kIt][3];
 #pragma unroll
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
 #endif
                 }
             }
-        } else
+        } else {
+        if (WARP) __syncthreads();   // base-grid table ready
 #pragma unroll
         for (int it = 0; it < (kRN + kThreads - 1) / kThreads; ++it) {
             const int q = tid + it * kThreads;
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                 if (WARP) sm.flow[q] = fl;
 #endif
             }
+        }
         }
         if (WARP && has_lay) {
             bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
@@ -713,7 +716,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
     // the result does not depend on which CTA happens to be last)
     if (p.red.out != nullptr) {
         __shared__ int s_last;
-        __threadfence();                 // publish this thread's partials / maxima
+        if (tid < kPartialSlots || tid == 32) __threadfence();   // only the threads that wrote partials / maxima
         __syncthreads();
         if (tid == 0) s_last = atomicAdd(&p.hdr->blocks_done, 1u) == gridDim.x * gridDim.y * gridDim.z - 1;
         __syncthreads();
