@@ -189,6 +189,8 @@ CASES = [
     (1, 375, 1242, 20, 48.0, "soft", 0.05, 0.1, "border"),     # KITTI-shaped, large displacement + outliers
     (2, 67, 129, 20, 12.0, "soft", 0.0, 1.0, "zeros"),         # ragged tiles, zeros padding
     (1, 33, 35, 5, 2.0, "soft", 0.0, 0.0, "border"),           # small K
+    (1, 41, 70, 19, 3.0, "soft", 0.02, 0.3, "border"),         # 19 train ids, odd K (scalar channel path)
+    (1, 41, 70, 30, 3.0, "onehot", 0.02, 0.3, "zeros"),        # 29+1 classes of src/models/simple.py
 ]
 
 

@@ -11,9 +11,10 @@
 
 using namespace vlg;
 
-// Layout class counts compiled in (Cityscapes trainer: 20, src/models/gridnet.py:9; the others
-// cover the reference's alternative heads and the small-K parity fixtures).
-#define VLG_FOR_EACH_K(X) X(20) X(5)
+// Layout class counts compiled in: 20 = Cityscapes trainer head (src/models/gridnet.py:9), 19 = its
+// train ids without "None", 30 = the 29+1 classes of the earlier head (src/models/simple.py:19,42),
+// 5 = small-K parity fixture.
+#define VLG_FOR_EACH_K(X) X(20) X(19) X(30) X(5)
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
