@@ -1,0 +1,61 @@
+"""Property / fuzz tests on the GPU (hypothesis): random small shapes -- ragged tiles, 2-pixel images,
+both paddings, flow and grid coordinates, ignored labels -- against the torch oracle."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import vlg_b200
+from vlg_b200 import _cabi
+from oracle import torch_oracle as TO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cl(t):
+    return t.to(DEV).contiguous(memory_format=torch.channels_last)
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(N=st.integers(1, 2), H=st.integers(2, 37), W=st.integers(2, 70), K=st.sampled_from([5, 20]),
+       padding=st.sampled_from(["border", "zeros"]), as_grid=st.booleans(),
+       sigma=st.sampled_from([0.0, 0.4, 2.0, 9.0]), seed=st.integers(0, 2 ** 16), ignore=st.booleans())
+def test_fuzz_warp_loss_against_oracle(N, H, W, K, padding, as_grid, sigma, seed, ignore):
+    g = torch.Generator().manual_seed(seed)
+    src_rgb = torch.randn(N, 3, H, W, generator=g)
+    src_lay = torch.randn(N, K, H, W, generator=g)
+    tgt_rgb = torch.randn(N, 3, H, W, generator=g)
+    label = torch.randint(0, K, (N, H, W), generator=g)
+    if ignore:
+        label[torch.rand(N, H, W, generator=g) < 0.2] = -100
+        if (label != -100).sum() == 0:
+            label[0, 0, 0] = 0
+    flow = torch.randn(N, H, W, 2, generator=g) * sigma
+    coords = TO.flow_to_grid(flow) if as_grid else flow
+    w_tv = 0.0 if as_grid else 0.7
+    has_ssim = H >= 3 and W >= 3
+
+    # oracle (SSIM is undefined below 3x3: the product reports 0 for it, the reference would raise)
+    a, b, c = (t.clone().requires_grad_(True) for t in (src_rgb, src_lay, coords))
+    grid = c if as_grid else TO.flow_to_grid(c)
+    w_rgb, w_lay = TO.warp(a, grid, padding), TO.warp(b, grid, padding)
+    terms = [TO.l1_loss(w_rgb, tgt_rgb), TO.gradient_loss(w_rgb, tgt_rgb),
+             TO.ssim_loss(w_rgb, tgt_rgb) if has_ssim else torch.zeros(()), TO.cross_entropy(w_lay, label),
+             TO.flow_tv(c) if (not as_grid and H > 1 and W > 1) else torch.zeros(())]
+    total = 40 * terms[0] + 20 * (terms[1] + terms[2]) + 10 * terms[3] + w_tv * terms[4]
+    total.backward()
+
+    ga, gb, gc = _cl(src_rgb).requires_grad_(True), _cl(src_lay).requires_grad_(True), coords.to(DEV).requires_grad_(True)
+    cfg = vlg_b200.WarpLossConfig(w_tv=w_tv, padding_mode=padding, coords_are_grid=as_grid, want_argmax=True)
+    tot, vec, arg = vlg_b200.warp_loss(ga, gb, gc, _cl(tgt_rgb), label.to(DEV), cfg)
+    tot.backward()
+
+    got = vec.cpu().numpy().astype(np.float64)
+    want = np.array([t.item() for t in terms])
+    np.testing.assert_allclose(got[:5], want, rtol=2e-5, atol=1e-6)
+    assert torch.equal(arg.cpu(), torch.argmax(w_lay.detach(), 1))
+    for name, x, r in (("d_coords", gc.grad, c.grad), ("d_src_rgb", ga.grad, a.grad), ("d_src_layout", gb.grad, b.grad)):
+        err = (x.detach().float().cpu().contiguous() - r).abs().max().item()
+        scale = max(r.abs().max().item(), 1e-12)
+        assert err <= 2e-5 * scale, (name, err, scale, (N, H, W, K, padding, as_grid, sigma, seed))
