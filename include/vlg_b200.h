@@ -49,6 +49,7 @@ extern "C" {
 
 /* flags */
 #define VLG_FLAG_NO_FAR_PATH 1u /* caller asserts |displacement| < VLG_NEAR_RADIUS; far taps raise status */
+#define VLG_FLAG_NO_TMA 2u      /* stage the source-layout window with cp.async instead of a TMA tensor map   */
 
 /* term_mask bits */
 #define VLG_TERM_L1 1u

@@ -469,3 +469,21 @@ def test_class_weighted_cross_entropy_variants():
     wl = TO.warp(rb, TO.flow_to_grid(d["flow"]))
     ce = torch.nn.functional.cross_entropy(wl, d["tgt_label"], weight=w)
     np.testing.assert_allclose(vec[_cabi.LOSS_CE].item(), ce.item(), rtol=RTOL)
+
+
+def test_tma_and_cp_async_staging_agree_bitwise():
+    """The TMA tensor-map staging of the layout window (fp32, K % 4 == 0) and the cp.async fallback
+    feed the same bit-exact FMA chain: losses, argmax and all gradients must be identical."""
+    for sigma, padding in ((2.0, "border"), (5.0, "zeros")):
+        d = _make_case(2, 77, 141, 20, sigma, seed=13, layout="soft")
+        res = []
+        for tma in (True, False):
+            a = _cl(d["src_rgb"]).requires_grad_(True)
+            b = _cl(d["src_layout"]).requires_grad_(True)
+            f = d["flow"].to(DEV).requires_grad_(True)
+            cfg = vlg_b200.WarpLossConfig(w_tv=0.4, padding_mode=padding, use_tma=tma, want_argmax=True)
+            total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV), cfg)
+            total.backward()
+            res.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+        for x, y in zip(*res):
+            assert torch.equal(x, y)

@@ -281,8 +281,45 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, i
 }
 
 // ------------------------------------------------------------------ dispatch helpers
+// cuTensorMapEncodeTiled is fetched through the runtime (no -lcuda): NULL if the driver lacks it
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        (void)cudaGetLastError();
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// Tensor map of the NHWC source layout [N][H][W][K] with a kSW x kSH x K box: the window a pass-1 CTA
+// stages.  Returns false when TMA cannot be used (bf16 K=20 rows are not 16-byte multiples, odd K, ...).
+static bool make_layout_map(const vlg_problem_t *prob, const void *src_layout, CUtensorMap *map) {
+    memset(map, 0, sizeof(*map));
+    const size_t es = 4;
+    if (prob->dtype != VLG_F32 || (prob->K * es) % 16 != 0 || prob->K > 256) return false;
+    if (((uintptr_t)src_layout) % 16 != 0) return false;
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[4] = {(cuuint64_t)prob->K, (cuuint64_t)prob->W, (cuuint64_t)prob->H, (cuuint64_t)prob->N};
+    const cuuint64_t gstr[3] = {(cuuint64_t)prob->K * es, (cuuint64_t)prob->W * prob->K * es,
+                                (cuuint64_t)prob->H * prob->W * prob->K * es};
+    const cuuint32_t box[4] = {(cuuint32_t)prob->K, (cuuint32_t)kSW, (cuuint32_t)kSH, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(src_layout), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 template <typename T, int K>
-static int launch_pass1(bool warp, const Pass1Params &pp, int64_t n_blocks, cudaStream_t st) {
+static int launch_pass1(bool warp, const Pass1Params &pp, const CUtensorMap &lay_map, int64_t n_blocks, cudaStream_t st) {
     // the staged source window is the last member: the un-warped criteria do not allocate it
     using Smem = Pass1Smem<T, K>;
     const size_t smem_warp = sizeof(Smem), smem_plain = offsetof(Smem, stage);
@@ -296,16 +333,17 @@ static int launch_pass1(bool warp, const Pass1Params &pp, int64_t n_blocks, cuda
     }
     const dim3 grid((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N);
     (void)n_blocks;
-    if (warp) pass1_kernel<T, K, true><<<grid, kThreads, smem_warp, st>>>(pp);
-    else pass1_kernel<T, K, false><<<grid, kThreads, smem_plain, st>>>(pp);
+    if (warp) pass1_kernel<T, K, true><<<grid, kThreads, smem_warp, st>>>(pp, lay_map);
+    else pass1_kernel<T, K, false><<<grid, kThreads, smem_plain, st>>>(pp, lay_map);
     return check_launch("pass1_kernel");
 }
 
-static int dispatch_pass1(const vlg_problem_t *prob, bool warp, const Pass1Params &pp, int64_t n_blocks, cudaStream_t st) {
+static int dispatch_pass1(const vlg_problem_t *prob, bool warp, const Pass1Params &pp, const CUtensorMap &lay_map,
+                          int64_t n_blocks, cudaStream_t st) {
 #define X(k)                                                                              \
     if (prob->K == k) {                                                                   \
-        return prob->dtype == VLG_F32 ? launch_pass1<float, k>(warp, pp, n_blocks, st)    \
-                                      : launch_pass1<__nv_bfloat16, k>(warp, pp, n_blocks, st); \
+        return prob->dtype == VLG_F32 ? launch_pass1<float, k>(warp, pp, lay_map, n_blocks, st)    \
+                                      : launch_pass1<__nv_bfloat16, k>(warp, pp, lay_map, n_blocks, st); \
     }
     VLG_FOR_EACH_K(X)
 #undef X
@@ -394,7 +432,10 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
     pp.hdr = hdr;
     pp.flags = prob->flags;
-    return dispatch_pass1(prob, warp, pp, L.n_blocks, st);
+    CUtensorMap lay_map;
+    pp.use_tma = (warp && has_lay && !(prob->flags & VLG_FLAG_NO_TMA) && make_layout_map(prob, src_layout, &lay_map)) ? 1 : 0;
+    if (!pp.use_tma) memset(&lay_map, 0, sizeof(lay_map));
+    return dispatch_pass1(prob, warp, pp, lay_map, L.n_blocks, st);
 }
 
 template <typename T, int K>

@@ -22,6 +22,8 @@
 //       softmax-CE with ex2/lg2.approx, coordinate gradient, TV, stores
 //   3   block reduction -> one row of partial sums, per-tile displacement maxima
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is resolved at run time, libcuda is not linked)
+
 #include "vlg_device.cuh"
 
 namespace vlg {
@@ -56,6 +58,7 @@ struct Pass1Params {
     ReduceParams red;       // red.out != NULL: the last CTA also performs the final reduction
     WsHeader *hdr;
     uint32_t flags;
+    int use_tma;            // the layout window is staged by one cp.async.bulk.tensor per CTA
 };
 
 #ifndef VLG_P1_MIN_BLOCKS
@@ -86,7 +89,8 @@ struct Pass1Smem {
     float red[kThreads / 32][kPartialSlots];
     float redmax[kThreads / 32][4];
     int bbox[4];            // min x0, min y0, max x0, max y0 of the tile's own taps
-    alignas(16) T stage[kSH * kSW * K];
+    alignas(8) uint64_t tma_bar;           // mbarrier the TMA load of the layout window completes on
+    alignas(128) T stage[kSH * kSW * K];   // staged source-layout window
 };
 static_assert(sizeof(float2) * 3 * kRN + sizeof(float) * 9 * kWN >= 6 * 256 * sizeof(double),
               "ab (+flow) + k must hold the final-reduction scratch");
@@ -101,6 +105,37 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: one instruction per CTA stages the whole layout window,
+// out-of-image elements are zero-filled by the hardware (exactly the padding the gather wants)
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 
 // sampling coordinates from raw coords + the smem base-grid table
@@ -161,8 +196,8 @@ __device__ __forceinline__ float tap_global(const T *img, int C, int c, int y, i
 }
 
 template <typename T, int K, bool WARP>
-__global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(const Pass1Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(const Pass1Params p, const __grid_constant__ CUtensorMap lay_map) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Pass1Smem<T, K> &sm = *reinterpret_cast<Pass1Smem<T, K> *>(smem_raw);
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
@@ -202,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         if (tid < kRW) sm.bx[tid] = base_coord(tx0 - kHalo + tid, cc.Wm1);
         else if (tid >= 64 && tid < 64 + kRH) sm.by[tid - 64] = base_coord(ty0 - kHalo + tid - 64, cc.Hm1);
         if (tid == 128) { sm.bbox[0] = 1 << 30; sm.bbox[1] = 1 << 30; sm.bbox[2] = -(1 << 30); sm.bbox[3] = -(1 << 30); }
+        if (tid == 160 && p.use_tma) mbar_init(&sm.tma_bar, 1);
         // (the barrier that publishes the table sits in phase 0b, after the coords loads were issued)
     }
 
@@ -332,7 +368,14 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         sh = min(kSH, sm.bbox[3] + 2 - oy);
         constexpr int PXB = K * (int)sizeof(T);
         constexpr int VB = vec_bytes(PXB);
-        if (sw > 0 && sh > 0) {
+        if (p.use_tma) {
+            // one elected thread: the full kSW x kSH window at (ox, oy) of image n, zero-filled outside
+            sw = kSW; sh = kSH;
+            if (tid == 0) {
+                mbar_expect_tx(&sm.tma_bar, (unsigned)(kSH * kSW * PXB));
+                tma_load_4d(sm.stage, &lay_map, &sm.tma_bar, 0, ox, oy, n);
+            }
+        } else if (sw > 0 && sh > 0) {
             const int xa = min(max(0, ox), ox + sw), xb = max(min(ox + sw, W), xa);   // in-image columns [xa, xb)
             for (int ry = wid; ry < sh; ry += kThreads / 32) {
                 const int y = oy + ry;
@@ -421,7 +464,10 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
             }
         }
     }
-    if (WARP && has_lay) cp_async_commit_wait_all();
+    if (WARP && has_lay) {
+        if (p.use_tma) mbar_wait(&sm.tma_bar, 0);
+        else cp_async_commit_wait_all();
+    }
     __syncthreads();
 
     // ---------------- phase 2: own pixel ----------------

@@ -70,7 +70,7 @@ constexpr size_t pass2_smem_bytes() {
 
 template <typename T, int K>
 __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_lay = reinterpret_cast<float *>(smem_raw);                 // [kQN][K]   (16-byte aligned rows)
     float2 *s_xy = reinterpret_cast<float2 *>(s_lay + (size_t)kQN * K); // [kQN] source coords (NaN = skip)
     float *s_rgb = reinterpret_cast<float *>(s_xy + kQN);              // [kQN][3]
