@@ -300,17 +300,18 @@ static EncodeTiledFn tensor_map_encoder() {
 
 // Tensor map of the NHWC source layout [N][H][W][K] with a kSW x kSH x K box: the window a pass-1 CTA
 // stages.  Returns false when TMA cannot be used (bf16 K=20 rows are not 16-byte multiples, odd K, ...).
-static bool make_layout_map(const vlg_problem_t *prob, const void *src_layout, CUtensorMap *map) {
+static bool make_layout_map(const vlg_problem_t *prob, const void *src_layout, CUtensorMap *map, int box_w = kSW,
+                            int box_h = kSH, bool fp32_storage = false) {
     memset(map, 0, sizeof(*map));
     const size_t es = 4;
-    if (prob->dtype != VLG_F32 || (prob->K * es) % 16 != 0 || prob->K > 256) return false;
+    if ((prob->dtype != VLG_F32 && !fp32_storage) || (prob->K * es) % 16 != 0 || prob->K > 256) return false;
     if (((uintptr_t)src_layout) % 16 != 0) return false;
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint64_t gdim[4] = {(cuuint64_t)prob->K, (cuuint64_t)prob->W, (cuuint64_t)prob->H, (cuuint64_t)prob->N};
     const cuuint64_t gstr[3] = {(cuuint64_t)prob->K * es, (cuuint64_t)prob->W * prob->K * es,
                                 (cuuint64_t)prob->H * prob->W * prob->K * es};
-    const cuuint32_t box[4] = {(cuuint32_t)prob->K, (cuuint32_t)kSW, (cuuint32_t)kSH, 1u};
+    const cuuint32_t box[4] = {(cuuint32_t)prob->K, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(src_layout), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -351,7 +352,7 @@ static int dispatch_pass1(const vlg_problem_t *prob, bool warp, const Pass1Param
 }
 
 template <typename T, int K>
-static int launch_pass2(const Pass2Params &pp, int64_t n_blocks, int64_t P, const vlg_problem_t *prob, size_t far_words, cudaStream_t st) {
+static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_problem_t *prob, size_t far_words, cudaStream_t st) {
     (void)P; (void)far_words; (void)prob;
     if (pp.far_acc) {   // both exit at once unless pass 1 queued far pixels
         far_zero_kernel<K><<<148 * 2, kThreads, 0, st>>>(pp);
@@ -369,7 +370,12 @@ static int launch_pass2(const Pass2Params &pp, int64_t n_blocks, int64_t P, cons
         attr_done = true;
     }
     (void)n_blocks;
-    pass2_kernel<T, K><<<dim3((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N), kThreads, smem, st>>>(pp);
+    // the fp32 d_out staging buffer as a [N][H][W][K] tensor with a kQW x kQH window box
+    CUtensorMap dout_map;
+    pp.use_tma = (pp.d_src_lay && pp.d_out_lay && !(prob->flags & VLG_FLAG_NO_TMA) &&
+                  make_layout_map(prob, pp.d_out_lay, &dout_map, kQW, kQH, true)) ? 1 : 0;
+    if (!pp.use_tma) memset(&dout_map, 0, sizeof(dout_map));
+    pass2_kernel<T, K><<<dim3((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N), kThreads, smem, st>>>(pp, dout_map);
     return check_launch("pass2_kernel");
 }
 

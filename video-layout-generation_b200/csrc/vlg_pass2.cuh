@@ -34,6 +34,7 @@ struct Pass2Params {
     const float *tile_disp;   // [n_blocks] per-tile max NEAR displacement written by pass 1
     WsHeader *hdr;
     int64_t HW;
+    int use_tma;              // d_out_lay window staged by one cp.async.bulk.tensor per CTA
 };
 
 // Gather radius of one source tile: output pixels that can reach it lie within kRMax pixels, i.e.
@@ -69,12 +70,13 @@ constexpr size_t pass2_smem_bytes() {
 }
 
 template <typename T, int K>
-__global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
+__global__ void __launch_bounds__(kThreads, 4) pass2_kernel(const Pass2Params p, const __grid_constant__ CUtensorMap dout_map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_lay = reinterpret_cast<float *>(smem_raw);                 // [kQN][K]   (16-byte aligned rows)
     float2 *s_xy = reinterpret_cast<float2 *>(s_lay + (size_t)kQN * K); // [kQN] source coords (NaN = skip)
     float *s_rgb = reinterpret_cast<float *>(s_xy + kQN);              // [kQN][3]
     __shared__ float s_bx[kQW], s_by[kQH];   // base-grid table: one IEEE division per row / column
+    __shared__ alignas(8) uint64_t s_bar;    // mbarrier of the TMA window load
 
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
@@ -85,6 +87,13 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     const int ty0 = blockIdx.y * kTH, tx0 = blockIdx.x * kTW;
     const int64_t img_px = (int64_t)n * H * W;
 
+    // TMA first: the fixed window does not depend on anything loaded from memory
+    if (p.use_tma && p.d_src_lay != nullptr && p.d_out_lay != nullptr && tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_expect_tx(&s_bar, (unsigned)(kQN * K * sizeof(float)));
+        tma_load_4d(s_lay, &dout_map, &s_bar, 0, tx0 - kRMax, ty0 - kRMax, n);
+    }
     const uint32_t tile_far = p.far_acc ? __ldg(p.tile_flags + bt) : 0u;   // consumed at the very end: issue early
     const int r = near_radius(p, n, blockIdx.y, blockIdx.x);
     const int qw = kTW + 2 * r, qh = kTH + 2 * r;
@@ -92,20 +101,25 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
     const bool want_lay = p.d_src_lay != nullptr && p.d_out_lay != nullptr;
     const int xa = max(tx0 - r, 0), xb = min(tx0 - r + qw, W);   // in-image columns of the candidate region
 
-    // ---- stage d_out of the candidate region: one warp per row, contiguous cp.async ----
+    // ---- stage d_out of the candidate region ----
+    // The layout part always lives in a FIXED window of kQW x kQH pixels anchored at
+    // (tx0 - kRMax, ty0 - kRMax): with TMA it is one cp.async.bulk.tensor issued before anything else
+    // (no dependence on the per-tile radius), otherwise cp.async row copies of the needed sub-window.
+    const int lay_off = (kRMax - r) * kQW + (kRMax - r);   // window cell of region pixel (0, 0)
     for (int ry = wid; ry < qh; ry += kThreads / 32) {
         const int y = ty0 - r + ry;
         if (y < 0 || y >= H || xb <= xa) continue;
         const int64_t g0 = img_px + (int64_t)y * W + xa;
         const int q0 = ry * qw + (xa - (tx0 - r));
-        if (want_lay) {
+        if (want_lay && !p.use_tma) {
+            const int c0 = lay_off + ry * kQW + (xa - (tx0 - r));
             const char *src = reinterpret_cast<const char *>(p.d_out_lay + g0 * K);
-            char *dst = reinterpret_cast<char *>(s_lay + (size_t)q0 * K);
+            char *dst = reinterpret_cast<char *>(s_lay + (size_t)c0 * K);
             const int nbytes = (xb - xa) * K * 4;
             if constexpr (K % 4 == 0) {
                 for (int i = lane * 16; i < nbytes; i += 32 * 16) cp_async16(dst + i, src + i);
             } else {
-                for (int i = lane; i < (xb - xa) * K; i += 32) s_lay[(size_t)q0 * K + i] = __ldg(p.d_out_lay + g0 * K + i);
+                for (int i = lane; i < (xb - xa) * K; i += 32) s_lay[(size_t)c0 * K + i] = __ldg(p.d_out_lay + g0 * K + i);
             }
         }
         if (want_rgb)   // 12-byte pixels: 4-byte cp.async (no register round trip, completes with the group)
@@ -154,6 +168,7 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
         }
     }
     cp_async_commit_wait_all();
+    if (want_lay && p.use_tma) mbar_wait(&s_bar, 0);
     __syncthreads();
 
     // ---- one thread per source pixel: fixed-order gather ----
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(const Pass2Params p) {
             const float w = __fmul_rn(wx, wy);
             if (want_lay) {
                 float v[K];
-                load_px_smem<float, K>(s_lay + (size_t)q * K, v);
+                load_px_smem<float, K>(s_lay + (size_t)(lay_off + (ty + r + dy) * kQW + tx + j) * K, v);
                 fma2_bcast<K>(acc_l, v, w);
             }
             if (want_rgb) {
