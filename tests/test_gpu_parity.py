@@ -472,8 +472,9 @@ def test_class_weighted_cross_entropy_variants():
 
 
 def test_tma_and_cp_async_staging_agree_bitwise():
-    """The TMA tensor-map staging of the layout window (fp32, K % 4 == 0) and the cp.async fallback
-    feed the same bit-exact FMA chain: losses, argmax and all gradients must be identical."""
+    """Inside the tile kernel, the TMA tensor-map staging of the layout window (fp32, K % 4 == 0) and
+    the cp.async fallback feed the same bit-exact FMA chain: losses, argmax and all gradients must be
+    identical."""
     for sigma, padding in ((2.0, "border"), (5.0, "zeros")):
         d = _make_case(2, 77, 141, 20, sigma, seed=13, layout="soft")
         res = []
@@ -481,9 +482,35 @@ def test_tma_and_cp_async_staging_agree_bitwise():
             a = _cl(d["src_rgb"]).requires_grad_(True)
             b = _cl(d["src_layout"]).requires_grad_(True)
             f = d["flow"].to(DEV).requires_grad_(True)
-            cfg = vlg_b200.WarpLossConfig(w_tv=0.4, padding_mode=padding, use_tma=tma, want_argmax=True)
+            cfg = vlg_b200.WarpLossConfig(w_tv=0.4, padding_mode=padding, use_tma=tma, want_argmax=True, tile_kernels=True)
             total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV), cfg)
             total.backward()
             res.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
         for x, y in zip(*res):
             assert torch.equal(x, y)
+
+
+def test_strip_and_tile_kernels_agree():
+    """The per-warp strip kernels (register pipeline for the rgb terms, TMA row ring for the layout)
+    and the 32x8 tile kernel are two schedules of the same arithmetic: argmax layouts and
+    d(loss)/d(warped layout) -- hence d_src_layout -- are bit-identical (same FMA chain, same softmax
+    instruction sequence); sums that are associated differently agree to rounding."""
+    for sigma, padding, shape in ((0.6, "border", (2, 77, 141)), (5.0, "zeros", (2, 77, 141)), (2.0, "border", (1, 19, 33)),
+                                  (9.0, "border", (3, 64, 200))):
+        d = _make_case(*shape, 20, sigma, seed=17, layout="soft")
+        res = []
+        for tile in (False, True):
+            a = _cl(d["src_rgb"]).requires_grad_(True)
+            b = _cl(d["src_layout"]).requires_grad_(True)
+            f = d["flow"].to(DEV).requires_grad_(True)
+            cfg = vlg_b200.WarpLossConfig(w_tv=0.4, padding_mode=padding, want_argmax=True, tile_kernels=tile)
+            total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV), cfg)
+            total.backward()
+            res.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+        (v0, arg0, ga0, gb0, gf0), (v1, arg1, ga1, gb1, gf1) = res
+        assert torch.equal(arg0, arg1)
+        assert torch.equal(gb0, gb1)
+        np.testing.assert_allclose(v0[:6].cpu().numpy(), v1[:6].cpu().numpy(), rtol=2e-6)
+        for name, x, y in (("d_src_rgb", ga0, ga1), ("d_flow", gf0, gf1)):
+            err = (x - y).abs().max().item()
+            assert err <= 1e-5 * y.abs().max().item(), (name, err)   # the parity bar; typical 3e-6 (SSIM adjoint, rcp.approx)

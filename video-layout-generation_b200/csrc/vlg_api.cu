@@ -1,6 +1,7 @@
 // vlg_api.cu -- the C ABI declared in include/vlg_b200.h: argument checks, workspace carving,
 // kernel launches.  No allocation, no host synchronisation (except vlg_read_status), no torch.
 #include <atomic>
+#include <climits>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -8,6 +9,8 @@
 
 #include "vlg_pass1.cuh"
 #include "vlg_pass2.cuh"
+#include "vlg_rgb.cuh"
+#include "vlg_lay.cuh"
 
 using namespace vlg;
 
@@ -64,9 +67,12 @@ static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
     L.n_blocks = p->N * tiles_x(p->W) * tiles_y(p->H);
     size_t off = 0;
     L.header = off; off = align_up(off + sizeof(WsHeader), 256);
-    L.tile_flags = off; off = align_up(off + (size_t)L.n_blocks * sizeof(uint32_t), 256);   // zeroed together with the header
-    L.partials = off; off = align_up(off + (size_t)L.n_blocks * kPartialSlots * sizeof(float), 256);
+    // header, per-tile far flags and per-tile displacement maxima are contiguous: one memset resets all three
+    L.tile_flags = off; off = align_up(off + (size_t)L.n_blocks * sizeof(uint32_t), 256);
     L.tile_disp = off; off = align_up(off + (size_t)L.n_blocks * sizeof(float), 256);
+    L.partials = off; off = align_up(off + (size_t)L.n_blocks * kPartialSlots * sizeof(float), 256);
+    L.partials_rgb = off; off = align_up(off + (size_t)kRgbMaxWarps * kRgbSlots * sizeof(float), 256);
+    L.partials_lay = off; off = align_up(off + (size_t)kLayMaxWarps * 4 * sizeof(float), 256);
     L.flagged = off; off = align_up(off + (size_t)L.n_blocks * sizeof(int), 256);
     L.dout_rgb = L.dout_lay = L.far_acc = L.far_list = 0;
     if (with_src_grad) {
@@ -138,7 +144,7 @@ __global__ void count_valid_kernel(const int64_t *__restrict__ label, int64_t P,
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
     __shared__ double s[6 * 256];
-    reduce_partials_block(p, s);
+    reduce_partials_block<256>(p, s);
 }
 
 static ReduceParams make_reduce_params(const vlg_problem_t *prob, const WsLayout &L, char *ws, float *loss_out) {
@@ -146,7 +152,8 @@ static ReduceParams make_reduce_params(const vlg_problem_t *prob, const WsLayout
     const double H = (double)prob->H, W = (double)prob->W;
     ReduceParams rp{};
     rp.partials = (const float *)(ws + L.partials);
-    rp.n_blocks = L.n_blocks;
+    rp.partials_rgb = (const float *)(ws + L.partials_rgb);
+    rp.partials_lay = (const float *)(ws + L.partials_lay);
     rp.hdr = (const WsHeader *)(ws + L.header);
     rp.inv_numel_rgb = 1.0 / (Ng * 3 * H * W);
     rp.inv_ssim = (prob->H > 2 && prob->W > 2) ? 1.0 / (Ng * (H - 2) * (W - 2)) : 0.0;
@@ -389,13 +396,70 @@ static int launch_fwd(const vlg_problem_t *prob, const void *src_rgb, const void
     return check_launch("warp_fwd_kernel");
 }
 
+// Persistent-warp launch of the rgb strip kernel: one wave of resident warps, each with an equal
+// contiguous run of (image, strip, row).
+template <typename T>
+static int launch_rgb(RgbParams rp, bool grad, cudaStream_t st) {
+    static int warps_resident = 0;   // per instantiation (T); GRAD variants share the register budget
+    if (!warps_resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgb_strip_kernel<T, true>, kRgbThreads, 0);
+        if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "rgb_strip_kernel occupancy query: %s", cudaGetErrorString(e));
+        warps_resident = sms * per_sm * (kRgbThreads / 32);
+    }
+    int64_t warps = warps_resident < kRgbMaxWarps ? warps_resident : kRgbMaxWarps;
+    const int64_t min_rows = 12;   // shorter runs are dominated by the 4 warm-up rows of a segment
+    if (warps * min_rows > rp.total_rows) warps = (rp.total_rows + min_rows - 1) / min_rows;
+    const int64_t blocks = (warps + kRgbThreads / 32 - 1) / (kRgbThreads / 32);
+    rp.chunk = (rp.total_rows + blocks * (kRgbThreads / 32) - 1) / (blocks * (kRgbThreads / 32));
+    if (grad) rgb_strip_kernel<T, true><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
+    else rgb_strip_kernel<T, false><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
+    return check_launch("rgb_strip_kernel");
+}
+
+// Persistent-warp launch of the layout strip kernel (fp32 layouts with K % 4 == 0: TMA-able rows).
+template <int K>
+static int launch_lay(LayParams lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
+    using WS = LayWarpSmem<float, K>;
+    const size_t smem = sizeof(WS) * kLayWarps;
+    static int warps_resident = 0;
+    if (!warps_resident) {
+        cudaError_t e = cudaFuncSetAttribute(lay_strip_kernel<float, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lay_strip_kernel<float, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int dev = 0, sms = 0, per_sm = 0;
+        if (e == cudaSuccess) e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lay_strip_kernel<float, K, true>, kLayThreads, smem);
+        if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "lay_strip_kernel setup: %s", cudaGetErrorString(e));
+        warps_resident = sms * per_sm * kLayWarps;
+    }
+    int64_t warps = warps_resident < kLayMaxWarps ? warps_resident : kLayMaxWarps;
+    const int64_t min_rows = 8;
+    if (warps * min_rows > lp.total_rows) warps = (lp.total_rows + min_rows - 1) / min_rows;
+    const int64_t blocks = (warps + kLayWarps - 1) / kLayWarps;
+    lp.chunk = (lp.total_rows + blocks * kLayWarps - 1) / (blocks * kLayWarps);
+    if (grad) lay_strip_kernel<float, K, true><<<(unsigned)blocks, kLayThreads, smem, st>>>(lp, map);
+    else lay_strip_kernel<float, K, false><<<(unsigned)blocks, kLayThreads, smem, st>>>(lp, map);
+    return check_launch("lay_strip_kernel");
+}
+
+static int dispatch_lay(const vlg_problem_t *prob, const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
+#define X(k) if constexpr ((k) % 4 == 0) { if (prob->K == k) return launch_lay<k>(lp, map, grad, st); }
+    VLG_FOR_EACH_K(X)
+#undef X
+    return fail(VLG_ERR_UNSUPPORTED, "layout strip kernel: K not compiled in");
+}
+
 static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, const void *src_layout,
                      const float *coords, const void *tgt_rgb, const int64_t *tgt_label, float *d_coords,
                      void *d_out_rgb, void *d_out_lay, bool need_grad, int64_t *out_argmax, float *fused_loss_out,
                      void *workspace, const WsLayout &L, cudaStream_t st) {
     char *ws = (char *)workspace;
     WsHeader *hdr = (WsHeader *)(ws + L.header);
-    // header + per-tile far flags are contiguous: one memset node resets both
+    // header + per-tile far flags + per-tile displacement maxima are contiguous: one memset node resets them
     cudaError_t e = cudaMemsetAsync(hdr, 0, L.partials - L.header, st);
     if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "memset header: %s", cudaGetErrorString(e));
     const int64_t P = prob->N * prob->H * prob->W;
@@ -438,6 +502,49 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
     pp.hdr = hdr;
     pp.flags = prob->flags;
+    if (warp && src_rgb && tgt_rgb && !(prob->flags & VLG_FLAG_TILE_RGB)) {
+        // the rgb terms run in the column-strip kernel; the tile kernel keeps the layout, TV and the
+        // final reduction, and adds its coordinate gradient to the one written here
+        RgbParams rp{};
+        rp.cc = pp.cc;
+        rp.N = (int)prob->N;
+        rp.strips = (int)((prob->W + kRS - 1) / kRS);
+        rp.total_rows = prob->N * rp.strips * prob->H;
+        rp.src_rgb = src_rgb; rp.tgt_rgb = tgt_rgb; rp.coords = coords;
+        rp.terms = pp.terms;
+        rp.c_l1 = (pp.terms & VLG_TERM_L1) ? pp.c_l1 : 0.f;
+        rp.c_gd = (pp.terms & VLG_TERM_GD) ? pp.c_gd : 0.f;
+        rp.c_ssim = (pp.terms & VLG_TERM_SSIM) ? pp.c_ssim : 0.f;
+        rp.d_coords = need_grad ? d_coords : nullptr;
+        rp.d_out_rgb = need_grad ? (float *)d_out_rgb : nullptr;
+        rp.partials = (float *)(ws + L.partials_rgb);
+        rp.hdr = hdr;
+        int rc = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
+        if (rc) return rc;
+        pp.src_rgb = nullptr; pp.tgt_rgb = nullptr; pp.d_out_rgb = nullptr;
+        pp.accum_dcoords = 1;
+    }
+    if (warp && has_lay && prob->dtype == VLG_F32 && prob->K % 4 == 0 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_TILE_LAYOUT))) {
+        CUtensorMap row_map;
+        if (make_layout_map(prob, src_layout, &row_map, kLBW, 1)) {
+            LayParams lp{};
+            lp.cc = pp.cc;
+            lp.N = pp.N; lp.strips = pp.tiles_x; lp.tiles_y = pp.tiles_y;
+            lp.total_rows = prob->N * (int64_t)lp.strips * prob->H;
+            lp.src_layout = src_layout; lp.coords = coords; lp.label = tgt_label; lp.ignore_index = prob->ignore_index;
+            lp.class_weight = pp.class_weight; lp.weighted_denom = pp.weighted_denom;
+            lp.w_ce_over_scale = pp.w_ce_over_scale;
+            lp.c_tvh = pp.c_tvh; lp.c_tvw = pp.c_tvw; lp.do_tv = pp.do_tv;
+            lp.accum_dcoords = pp.accum_dcoords;
+            lp.d_coords = need_grad ? d_coords : nullptr;
+            lp.d_out_lay = need_grad ? (float *)d_out_lay : nullptr;
+            lp.out_argmax = out_argmax;
+            lp.partials = (float *)(ws + L.partials_lay);
+            lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
+            lp.red = pp.red; lp.hdr = hdr;
+            return dispatch_lay(prob, lp, row_map, need_grad, st);
+        }
+    }
     CUtensorMap lay_map;
     pp.use_tma = (warp && has_lay && !(prob->flags & VLG_FLAG_NO_TMA) && make_layout_map(prob, src_layout, &lay_map)) ? 1 : 0;
     if (!pp.use_tma) memset(&lay_map, 0, sizeof(lay_map));

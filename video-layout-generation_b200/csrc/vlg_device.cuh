@@ -25,20 +25,25 @@ struct WsHeader {
     uint32_t blocks_done;   // pass-1 CTAs that have published their partial sums (last one reduces)
     uint32_t n_flagged;     // source tiles that receive far contributions (length of the flagged list)
     uint32_t count_done;    // label-count CTAs finished (the last one derives ce_denom)
-    uint32_t pad0;
+    uint32_t n_rgb;         // per-warp partial rows written by rgb_strip_kernel (0: it did not run)
     double ce_denom;        // divisor of the weighted CE sum: sum_k w_k * hist_k (VLG_CE_NORM_TORCH with weights)
-    uint32_t pad[20];
+    uint32_t n_tile;        // partial rows written by the tile kernel (pass1_kernel), 0: it did not run
+    uint32_t n_lay;         // per-warp partial rows written by lay_strip_kernel
+    uint32_t pad[18];
     unsigned long long hist[32];  // labels per class (only filled when class weights are given)
 };
 static_assert(sizeof(WsHeader) == 384, "header size");
 
 constexpr int kPartialSlots = 8;  // l1, gd, ssim, ce, tv_h, tv_w, n_valid(unused), spare
 
-// Final reduction of the per-CTA partial sums: fixed summation order (row index, then a fixed
-// tree), fp64 accumulation -> bitwise reproducible loss vector whatever the CTA schedule was.
+// Final reduction of the partial sums: fixed summation order (row index, then a fixed tree), fp64
+// accumulation -> bitwise reproducible loss vector whatever the CTA / warp schedule was.  Three
+// producers: the tile kernel (one row of 8 per CTA), the rgb strip kernel (l1, gd, ssim per warp)
+// and the layout strip kernel (ce, tv_h, tv_w per warp); each publishes its row count in the header.
 struct ReduceParams {
-    const float *partials;
-    int64_t n_blocks;
+    const float *partials;       // [hdr->n_tile][kPartialSlots]
+    const float *partials_rgb;   // [hdr->n_rgb][4]  (l1, gd, ssim, -)
+    const float *partials_lay;   // [hdr->n_lay][4]  (ce, tv_h, tv_w, -)
     const WsHeader *hdr;
     double inv_numel_rgb;   // 1/(Ng*3*H*W)
     double inv_ssim;        // 1/(Ng*(H-2)*(W-2))
@@ -49,30 +54,40 @@ struct ReduceParams {
     float *out;
 };
 
-// Called by all 256 threads of one CTA; `s` is 6*256 doubles of shared memory.
+// Called by all NT threads of one CTA; `s` is 6*NT doubles of shared memory.
+template <int NT>
 __device__ __forceinline__ void reduce_partials_block(const ReduceParams &p, double *s) {
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int64_t b = threadIdx.x; b < p.n_blocks; b += 256) {
+    const int64_t n_tile = __ldcg(&p.hdr->n_tile), n_rgb = __ldcg(&p.hdr->n_rgb), n_lay = __ldcg(&p.hdr->n_lay);
+    for (int64_t b = threadIdx.x; b < n_tile; b += NT) {
         const float4 lo = __ldcg(reinterpret_cast<const float4 *>(p.partials + b * kPartialSlots));
         const float2 hi = __ldcg(reinterpret_cast<const float2 *>(p.partials + b * kPartialSlots + 4));
         acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w; acc[4] += hi.x; acc[5] += hi.y;
     }
+    for (int64_t b = threadIdx.x; b < n_rgb; b += NT) {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.partials_rgb) + b);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z;
+    }
+    for (int64_t b = threadIdx.x; b < n_lay; b += NT) {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.partials_lay) + b);
+        acc[3] += v.x; acc[4] += v.y; acc[5] += v.z;
+    }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) s[i * 256 + threadIdx.x] = acc[i];
+    for (int i = 0; i < 6; ++i) s[i * NT + threadIdx.x] = acc[i];
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = NT / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o)
 #pragma unroll
-            for (int i = 0; i < 6; ++i) s[i * 256 + threadIdx.x] += s[i * 256 + threadIdx.x + o];
+            for (int i = 0; i < 6; ++i) s[i * NT + threadIdx.x] += s[i * NT + threadIdx.x + o];
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         const double nv = (double)__ldcg(&p.hdr->n_valid);
-        const double l1 = s[0] * p.inv_numel_rgb, gd = s[256] * p.inv_numel_rgb;
-        const double ssim = s[512] * p.inv_ssim;
+        const double l1 = s[0] * p.inv_numel_rgb, gd = s[NT] * p.inv_numel_rgb;
+        const double ssim = s[2 * NT] * p.inv_ssim;
         const double cd = p.weighted_denom ? __ldcg(&p.hdr->ce_denom) : nv;
-        const double ce = cd > 0 ? s[768] / cd * p.ce_scale : 0.0;
-        const double tv = s[1024] * p.inv_tvh + s[1280] * p.inv_tvw;
+        const double ce = cd > 0 ? s[3 * NT] / cd * p.ce_scale : 0.0;
+        const double tv = s[4 * NT] * p.inv_tvh + s[5 * NT] * p.inv_tvw;
         p.out[VLG_LOSS_L1] = (float)l1;
         p.out[VLG_LOSS_GD] = (float)gd;
         p.out[VLG_LOSS_SSIM] = (float)ssim;
@@ -96,7 +111,7 @@ __host__ __device__ __forceinline__ int64_t dout_index(int64_t n, int64_t HW, in
 }
 
 struct WsLayout {
-    size_t header, tile_flags, partials, tile_disp, flagged, dout_rgb, dout_lay, far_acc, far_list, total;
+    size_t header, tile_flags, tile_disp, partials, partials_rgb, partials_lay, flagged, dout_rgb, dout_lay, far_acc, far_list, total;
     int64_t n_blocks;
 };
 
