@@ -492,9 +492,8 @@ def test_tma_and_cp_async_staging_agree_bitwise():
 
 def test_strip_and_tile_kernels_agree():
     """The per-warp strip kernels (register pipeline for the rgb terms, TMA row ring for the layout)
-    and the 32x8 tile kernel are two schedules of the same arithmetic: argmax layouts and
-    d(loss)/d(warped layout) -- hence d_src_layout -- are bit-identical (same FMA chain, same softmax
-    instruction sequence); sums that are associated differently agree to rounding."""
+    and the 32x8 tile kernel are two schedules of the same arithmetic: argmax layouts are bit-identical
+    (same FMA chain); losses and gradients, whose sums are associated differently, agree to rounding."""
     for sigma, padding, shape in ((0.6, "border", (2, 77, 141)), (5.0, "zeros", (2, 77, 141)), (2.0, "border", (1, 19, 33)),
                                   (9.0, "border", (3, 64, 200))):
         d = _make_case(*shape, 20, sigma, seed=17, layout="soft")
@@ -509,8 +508,7 @@ def test_strip_and_tile_kernels_agree():
             res.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
         (v0, arg0, ga0, gb0, gf0), (v1, arg1, ga1, gb1, gf1) = res
         assert torch.equal(arg0, arg1)
-        assert torch.equal(gb0, gb1)
         np.testing.assert_allclose(v0[:6].cpu().numpy(), v1[:6].cpu().numpy(), rtol=2e-6)
-        for name, x, y in (("d_src_rgb", ga0, ga1), ("d_flow", gf0, gf1)):
+        for name, x, y in (("d_src_rgb", ga0, ga1), ("d_src_layout", gb0, gb1), ("d_flow", gf0, gf1)):
             err = (x - y).abs().max().item()
             assert err <= 1e-5 * y.abs().max().item(), (name, err)   # the parity bar; typical 3e-6 (SSIM adjoint, rcp.approx)

@@ -42,4 +42,12 @@ for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total):
     us = e.device_time_total / reps
     tot += us
     print(f"{us:9.1f} us  x{e.count / reps:4.1f}  {e.key[:110]}")
+hdr = ws[:384].cpu().numpy().view("uint64")
+prof = hdr[32:48]
+if prof.any():
+    names = ["plan:logic+tma", "taps+disp", "ring wait", "softmax", "grad dots", "obuf:issue", "tv+dcoords", "plan:ldg issue", "plan:xy+redux", "label+addr", "gather", "obuf:sts", "obuf:wait_read", "-", "-", "-"]
+    print(f"fallback lanes {int(prof[13])}, rows with a fallback lane {int(prof[14])} of {int(prof[15])} warp-rows")
+    prof = prof.copy(); prof[13:] = 0
+    tot_c = float(prof.sum())
+    print("lay_strip sections (cycles summed over warps, last step): " + ", ".join(f"{n} {c / tot_c * 100:.1f}%" for n, c in zip(names, prof) if c))
 print(f"{tot:9.1f} us  total per step   loss {loss.tolist()[:6]}")

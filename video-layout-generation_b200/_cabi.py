@@ -56,6 +56,9 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
+    override = os.environ.get("VLG_B200_LIB")   # kernel-tuning experiments: another build of this same library
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing and _build.is_stale():
         try:
             _build.build_library()

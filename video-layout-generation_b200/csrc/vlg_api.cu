@@ -17,7 +17,11 @@ using namespace vlg;
 // Layout class counts compiled in: 20 = Cityscapes trainer head (src/models/gridnet.py:9), 19 = its
 // train ids without "None", 30 = the 29+1 classes of the earlier head (src/models/simple.py:19,42),
 // 5 = small-K parity fixture.
+#ifdef VLG_FAST_BUILD   // kernel-tuning builds: the benchmark head only
+#define VLG_FOR_EACH_K(X) X(20)
+#else
 #define VLG_FOR_EACH_K(X) X(20) X(19) X(30) X(5)
+#endif
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -423,7 +427,11 @@ static int launch_rgb(RgbParams rp, bool grad, cudaStream_t st) {
 template <int K>
 static int launch_lay(LayParams lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
     using WS = LayWarpSmem<float, K>;
+#ifdef VLG_LAY_ONE_CTA   // tuning experiment: pad shared memory so that a single CTA fits an SM
+    const size_t smem = 200 * 1024;
+#else
     const size_t smem = sizeof(WS) * kLayWarps;
+#endif
     static int warps_resident = 0;
     if (!warps_resident) {
         cudaError_t e = cudaFuncSetAttribute(lay_strip_kernel<float, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -502,10 +510,12 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
     pp.hdr = hdr;
     pp.flags = prob->flags;
-    if (warp && src_rgb && tgt_rgb && !(prob->flags & VLG_FLAG_TILE_RGB)) {
-        // the rgb terms run in the column-strip kernel; the tile kernel keeps the layout, TV and the
-        // final reduction, and adds its coordinate gradient to the one written here
-        RgbParams rp{};
+    // The rgb terms run in the column-strip kernel, launched AFTER the kernel that owns the layout / TV
+    // terms: that one stores its part of d(loss)/d(coords), the strip kernel adds the rgb part (loaded a
+    // row ahead) and, being last, performs the final reduction of every partial sum.
+    const bool rgb_strips = warp && src_rgb && tgt_rgb && !(prob->flags & VLG_FLAG_TILE_RGB);
+    RgbParams rp{};
+    if (rgb_strips) {
         rp.cc = pp.cc;
         rp.N = (int)prob->N;
         rp.strips = (int)((prob->W + kRS - 1) / kRS);
@@ -519,11 +529,12 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
         rp.d_out_rgb = need_grad ? (float *)d_out_rgb : nullptr;
         rp.partials = (float *)(ws + L.partials_rgb);
         rp.hdr = hdr;
-        int rc = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
-        if (rc) return rc;
+        rp.red = pp.red;
+        pp.red.out = nullptr;
         pp.src_rgb = nullptr; pp.tgt_rgb = nullptr; pp.d_out_rgb = nullptr;
-        pp.accum_dcoords = 1;
     }
+    int rc = VLG_OK;
+    bool lay_done = false;
     if (warp && has_lay && prob->dtype == VLG_F32 && prob->K % 4 == 0 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_TILE_LAYOUT))) {
         CUtensorMap row_map;
         if (make_layout_map(prob, src_layout, &row_map, kLBW, 1)) {
@@ -535,20 +546,26 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.class_weight = pp.class_weight; lp.weighted_denom = pp.weighted_denom;
             lp.w_ce_over_scale = pp.w_ce_over_scale;
             lp.c_tvh = pp.c_tvh; lp.c_tvw = pp.c_tvw; lp.do_tv = pp.do_tv;
-            lp.accum_dcoords = pp.accum_dcoords;
             lp.d_coords = need_grad ? d_coords : nullptr;
             lp.d_out_lay = need_grad ? (float *)d_out_lay : nullptr;
             lp.out_argmax = out_argmax;
             lp.partials = (float *)(ws + L.partials_lay);
             lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
             lp.red = pp.red; lp.hdr = hdr;
-            return dispatch_lay(prob, lp, row_map, need_grad, st);
+            rc = dispatch_lay(prob, lp, row_map, need_grad, st);
+            if (rc) return rc;
+            lay_done = true;
         }
     }
-    CUtensorMap lay_map;
-    pp.use_tma = (warp && has_lay && !(prob->flags & VLG_FLAG_NO_TMA) && make_layout_map(prob, src_layout, &lay_map)) ? 1 : 0;
-    if (!pp.use_tma) memset(&lay_map, 0, sizeof(lay_map));
-    return dispatch_pass1(prob, warp, pp, lay_map, L.n_blocks, st);
+    if (!lay_done) {
+        CUtensorMap lay_map;
+        pp.use_tma = (warp && has_lay && !(prob->flags & VLG_FLAG_NO_TMA) && make_layout_map(prob, src_layout, &lay_map)) ? 1 : 0;
+        if (!pp.use_tma) memset(&lay_map, 0, sizeof(lay_map));
+        rc = dispatch_pass1(prob, warp, pp, lay_map, L.n_blocks, st);
+        if (rc) return rc;
+    }
+    if (rgb_strips) rc = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
+    return rc;
 }
 
 template <typename T, int K>

@@ -32,6 +32,22 @@
 
 namespace vlg {
 
+#ifdef VLG_LAY_PROFILE   // tuning builds only: per-section cycle counters (serialise the sections)
+#define VLG_PROF_DECL long long prof_acc[16] = {0}; long long prof_t = clock64();
+#define VLG_PROF_START prof_t = clock64();
+#define VLG_PROF(i) { const long long now_ = clock64(); prof_acc[i] += now_ - prof_t; prof_t = now_; }
+#define VLG_PROF_FLUSH if (lane == 0) { for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&p.hdr->hist[16 + i_], (unsigned long long)prof_acc[i_]); }
+#else
+#define VLG_PROF_DECL
+#define VLG_PROF_START
+#define VLG_PROF(i)
+#define VLG_PROF_FLUSH
+#endif
+
+#ifndef VLG_ABL
+#define VLG_ABL 0   // tuning builds: ablation bits (results are wrong when non-zero)
+#endif
+
 constexpr int kLW = 32;            // output columns per strip (== kTW: pass 2's tile width)
 constexpr int kLayThreads = 128;   // 4 independent warps per CTA
 constexpr int kLayWarps = kLayThreads / 32;
@@ -57,7 +73,6 @@ struct LayParams {
     float w_ce_over_scale;
     float c_tvh, c_tvw;
     int do_tv;
-    int accum_dcoords;             // d_coords already holds the rgb part
     float *d_coords;               // nullable (validation)
     float *d_out_lay;              // [P][K] fp32 staging, nullable
     int64_t *out_argmax;           // nullable
@@ -102,26 +117,27 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
     WS &sm = *reinterpret_cast<WS *>(smem_raw + (size_t)wib * sizeof(WS));
     constexpr int PXB = K * (int)sizeof(T);
     constexpr unsigned kRowBytes = (unsigned)(kLBW * PXB);
-    constexpr int OFF = 64;   // keeps (row + OFF) non-negative: tap rows are clamped to >= -4
 
     if (lane < kLR) mbar_init(&sm.bar[lane], 1);
     __syncwarp();
+    VLG_PROF_DECL
+    // Ring protocol (all warp-uniform): source rows are issued in increasing order, `top` is the next row
+    // to issue and lives in slot `slot_top`; rows below `ready` have been waited for.  Every load is
+    // waited for exactly once, in issue order (when a row needs it, before its slot is re-armed, or at
+    // the end of the segment), so an mbarrier never has two loads outstanding in one phase and no TMA
+    // write is in flight when shared memory is reused or released.
     unsigned issue_par = 0u;  // bit s: parity the NEXT load issued on slot s will complete
-    unsigned in_flight = 0u;  // bit s: a load was issued on slot s and nobody has waited for it yet
-    // every issued load is waited for exactly once (before its slot is re-armed, when a row samples it,
-    // or at the end of the segment), so an mbarrier never has two loads outstanding in one phase and no
-    // TMA write is in flight when the CTA's shared memory is reused or released
-    auto wait_slot = [&](int sl) {
-        mbar_wait(&sm.bar[sl], ((issue_par >> sl) & 1u) ^ 1u);
-        in_flight &= ~(1u << sl);
-    };
 
     int64_t rho = (int64_t)gw * p.chunk;
     const int64_t rho_end = min(rho + p.chunk, p.total_rows);
     float s_ce = 0.f, s_tvh = 0.f, s_tvw = 0.f;
     float m_disp = 0.f, m_grad = 0.f;
     const float denom = GRAD ? (p.weighted_denom ? (float)__ldcg(&p.hdr->ce_denom) : (float)__ldcg(&p.hdr->n_valid)) : 1.0f;
+    const float ce_unit = GRAD ? p.w_ce_over_scale / denom : 0.f;   // one division per thread, not one per pixel
     const T *src_all = reinterpret_cast<const T *>(p.src_layout);
+    const float mx_c = (cc.coord_mode == VLG_COORD_FLOW) ? __fmul_rn(cc.Wm1, 0.5f) * cc.sx : __fmul_rn(cc.Wm1, 0.5f);
+    const float my_c = (cc.coord_mode == VLG_COORD_FLOW) ? __fmul_rn(cc.Hm1, 0.5f) * cc.sy : __fmul_rn(cc.Hm1, 0.5f);
+    const bool border = cc.padding == VLG_PAD_BORDER;
 
     while (rho < rho_end) {
         // ---- one segment: rows [ya, yb) of strip s of image n ----
@@ -137,120 +153,147 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
         const int64_t img = (int64_t)n * H * W;
         const T *src_lay = src_all + img * K;
         const float2 *coords = reinterpret_cast<const float2 *>(p.coords) + img;
+        const int64_t *labels = p.label + img;
         const int npx = min(kLW, W - s * kLW);
+        const int ref_a = min(10, npx - 1), ref_b = min(21, npx - 1);   // the two lanes the ring follows
 
-        // ring state (warp-uniform)
-        int top = INT_MIN, lo = INT_MIN;        // source rows [max(lo, top - kLR), top) are resident / in flight
-        int pend_ymin[kLD + 1];                 // lowest source row needed by output rows t .. t+kLD
-#pragma unroll
-        for (int i = 0; i <= kLD; ++i) pend_ymin[i] = INT_MAX;
-        int row_ymin[kLD + 1], row_ymax[kLD + 1];   // bounding rows of output rows t .. t+kLD
-#pragma unroll
-        for (int i = 0; i <= kLD; ++i) { row_ymin[i] = INT_MAX; row_ymax[i] = INT_MIN; }
+        // lane-constant pieces of the TV stencil: coefficient = 0 where the neighbour does not exist
+        const float cR = (col_ok && x + 1 < W) ? p.c_tvw : 0.f, cL = (col_ok && x >= 1) ? p.c_tvw : 0.f;
+        const float mRt = (col_ok && x + 1 < W) ? 1.f : 0.f, mCol = col_ok ? 1.f : 0.f;
+        const float cV = col_ok ? p.c_tvh : 0.f;
+        const int xe = lane == 0 ? x - 1 : x + 1;                       // column of the strip's outer neighbour
+        const bool edge = p.do_tv && ((lane == 0 && x >= 1) || (lane == 31 && x + 1 < W));
 
-        auto load_flow = [&](int t) -> float2 {
-            return (t >= 0 && t < H) ? __ldg(coords + (t * W + xc)) : make_float2(0.f, 0.f);
+        // ring state
+        int top = 0, slot_top = 0, ready = 0, lo = 0;   // set by the first plan
+        bool ring_started = false;
+        int ref_y = 0, ref_dx = 0;                      // reference-lane tap row / column displacement of the last planned row
+
+        // base-grid y coordinates of 32 consecutive rows, one IEEE division per lane per 32 rows
+        int by_row0 = ya;
+        float by_tab = base_coord(by_row0 + lane, cc.Hm1);
+
+        auto load_flow = [&](int r) -> float2 {
+            return (r >= 0 && r < H) ? __ldg(coords + (r * W + xc)) : make_float2(0.f, 0.f);
         };
-        // plan + issue the ring loads output row u needs (stage B)
-        auto plan_row = [&](int u, float2 fl, int &ymin_o, int &ymax_o) {
-            ymin_o = INT_MAX; ymax_o = INT_MIN;
-            if (u < ya || u >= yb) return;
+        auto load_edge = [&](int r) -> float2 {   // flow of the column just outside the strip (lanes 0 and 31)
+            return (edge && r < H) ? __ldg(coords + (r * W + xe)) : make_float2(0.f, 0.f);
+        };
+        auto load_label = [&](int r) -> int64_t { return (r < yb) ? __ldg(labels + (r * W + xc)) : (int64_t)0; };
+        auto wait_next = [&]() {       // wait for the oldest issued row that nobody has waited for yet
+            int sl = slot_top - (top - ready);
+            sl = sl < 0 ? sl + kLR : sl;
+            mbar_wait(&sm.bar[sl], ((issue_par >> sl) & 1u) ^ 1u);
+            ++ready;
+        };
+        // sampling position of output row u + the ring loads it needs (stage B); returns the exclusive upper
+        // bound of the source rows the row samples, as far as the reference lanes tell
+        auto plan_row = [&](int u, float2 fl, float2 &xy_o, int &r_lo_o, int low_pending) -> int {
+            r_lo_o = INT_MAX;
+            if (u >= yb) return INT_MIN;
+            if (u - by_row0 >= 32) { by_row0 += 32; by_tab = base_coord(by_row0 + lane, cc.Hm1); }
             float mx, my;
-            const float2 xy = source_xy(cc, fl, bxv, base_coord(u, cc.Hm1), mx, my);
+            const float2 xy = source_xy(cc, fl, bxv, __shfl_sync(FULL, by_tab, u - by_row0), mx, my);
+            xy_o = xy;
             const int x0 = (int)fminf(fmaxf(floorf(xy.x), -4.0f), (float)W + 4.0f);
             const int y0 = (int)fminf(fmaxf(floorf(xy.y), -4.0f), (float)H + 4.0f);
-            int xmin = __reduce_min_sync(FULL, col_ok ? x0 : INT_MAX), xmax = __reduce_max_sync(FULL, col_ok ? x0 : INT_MIN);
-            int ymin = __reduce_min_sync(FULL, col_ok ? y0 : INT_MAX), ymax = __reduce_max_sync(FULL, col_ok ? y0 : INT_MIN);
-            if (ymax - ymin > kLR - 2 || xmax - xmin > kLBW - 2) {
-                // outliers: keep the lanes that move with the strip's centre lane
-                const int rx = __shfl_sync(FULL, x0 - x, min(15, npx - 1)), ry = __shfl_sync(FULL, y0, min(15, npx - 1));
-                const bool in = col_ok && abs(y0 - ry) <= (kLR - 2) / 2 && abs((x0 - x) - rx) <= (kLBW - kLW - 2) / 2;
-                xmin = __reduce_min_sync(FULL, in ? x0 : INT_MAX); xmax = __reduce_max_sync(FULL, in ? x0 : INT_MIN);
-                ymin = __reduce_min_sync(FULL, in ? y0 : INT_MAX); ymax = __reduce_max_sync(FULL, in ? y0 : INT_MIN);
+            // Follow two reference lanes instead of a bounding box (no warp reductions): of the two, the
+            // one closer to where the previous row was wins, so a single outlier does not derail the ring.
+            const int ya_ = __shfl_sync(FULL, y0, ref_a), yb_ = __shfl_sync(FULL, y0, ref_b);
+            const int xa_ = __shfl_sync(FULL, x0 - x, ref_a), xb_ = __shfl_sync(FULL, x0 - x, ref_b);
+            const int cont = ref_y + 1;
+            const bool pick_a = !ring_started || abs(ya_ - cont) <= abs(yb_ - cont);
+            const int ry = pick_a ? ya_ : yb_, rdx = pick_a ? xa_ : xb_;
+            const int r_lo = min(ry, ring_started ? min(ya_, yb_) : ry) - 1;   // one row of slack above
+            const int want_top = max(ya_, yb_) + 2;                            // rows < want_top hold the reference lanes' taps
+            r_lo_o = r_lo;
+            const int low_needed = min(r_lo, low_pending);                     // rows the not yet finished output rows sample
+            const int ox_new = s * kLW + rdx - (kLBW - kLW - 2) / 2;
+            ref_y = ry; ref_dx = rdx;
+            if (!ring_started || r_lo > top || r_lo < lo - 1) {
+                // first row of the segment, or the flow jumped: drain what is in flight and restart the ring
+                while (ready < top) wait_next();
+                top = ready = lo = r_lo;
+                slot_top = 0;
+                ring_started = true;
             }
-            ymin_o = ymin; ymax_o = ymax;
-            // rows [ymin, ymax + 1], columns [xmin, xmax + 1]; slack split evenly on both sides
-            const int ox_new = xmin - (kLBW - (xmax - xmin + 2)) / 2;
-            if (top == INT_MIN || ymin > top || ymin < lo) {   // first use, or the flow jumped: restart the resident range
-                top = ymin; lo = ymin;
+            if (top < want_top && top - kLR < low_needed) {
+                __syncwarp();
+                do {
+                    if (ready <= top - kLR) wait_next();          // the slot's previous load must have been waited for
+                    if (lane == 0) {
+                        sm.ox[slot_top] = ox_new;
+                        mbar_expect_tx(&sm.bar[slot_top], kRowBytes);
+                        tma_load_4d(sm.ring[slot_top], &lay_map, &sm.bar[slot_top], 0, ox_new, top, n);
+                    }
+                    issue_par ^= 1u << slot_top;
+                    ++top;
+                    slot_top = slot_top + 1 == kLR ? 0 : slot_top + 1;
+                } while (top < want_top && top - kLR < low_needed);   // never overwrite rows a pending output row samples
+                __syncwarp();
             }
-            int low_needed = ymin;
-#pragma unroll
-            for (int i = 0; i <= kLD; ++i) low_needed = min(low_needed, pend_ymin[i]);
-            __syncwarp();
-            while (top <= ymax + 1 && top - kLR < low_needed) {
-                const int sl = (top + OFF) % kLR;
-                if ((in_flight >> sl) & 1u) wait_slot(sl);
-                if (lane == 0) {
-                    sm.ox[sl] = ox_new;
-                    mbar_expect_tx(&sm.bar[sl], kRowBytes);
-                    tma_load_4d(sm.ring[sl], &lay_map, &sm.bar[sl], 0, ox_new, top, n);
-                }
-                issue_par ^= 1u << sl;
-                in_flight |= 1u << sl;
-                ++top;
-            }
-            __syncwarp();
+            return want_top;
         };
 
-        // ---- prologue: flows of rows ya .. ya+kLD+1, plans of rows ya .. ya+kLD-1 ----
+        // ---- prologue ----
+        // Loaded values are consumed at the TOP of the next iteration and the register is re-loaded right
+        // after: a value is never moved in the iteration that loads it (a move placed right behind its load
+        // exposes the whole memory latency -- measured: 18 % of all stall samples sat on one such MOV).
         int t = ya;
-        float2 fl[kLD + 2];
+        float2 fq[kLD + 1], xyq[kLD + 1];          // flows / sampling positions of rows t .. t+kLD
+        int wtq[kLD + 1], rlq[kLD + 1];            // their want_top / lowest sampled row (as far as the reference lanes tell)
 #pragma unroll
-        for (int i = 0; i < kLD + 2; ++i) fl[i] = load_flow(t + i);
-        int64_t lab[kLD + 1];
-        float2 dcp[kLD + 1];
-        auto load_aux = [&](int u, int64_t &l, float2 &d) {
-            l = 0; d = make_float2(0.f, 0.f);
-            if (u >= ya && u < yb) {
-                l = __ldg(p.label + img + (u * W + xc));
-                if (GRAD && p.accum_dcoords) d = __ldcg(reinterpret_cast<const float2 *>(p.d_coords) + img + (u * W + xc));
-            }
-        };
-#pragma unroll
-        for (int i = 0; i <= kLD; ++i) load_aux(t + i, lab[i], dcp[i]);
+        for (int i = 0; i <= kLD; ++i) { fq[i] = make_float2(0.f, 0.f); xyq[i] = make_float2(0.f, 0.f); wtq[i] = INT_MIN; rlq[i] = INT_MAX; }
 #pragma unroll
         for (int i = 0; i < kLD; ++i) {
-            plan_row(t + i, fl[i], row_ymin[i], row_ymax[i]);
-            pend_ymin[i] = row_ymin[i];
+            fq[i] = load_flow(t + i);
+            wtq[i] = plan_row(t + i, fq[i], xyq[i], rlq[i], i ? rlq[0] : INT_MAX);
         }
-        float2 fl_prev = load_flow(t - 1);      // TV stencil
-        int tile_row = -1;                      // 8-row tile the running maximum below belongs to
-        float m_near_tile = 0.f;
+        float2 pend_fl = load_flow(t + kLD);       // row t+kLD: planned at the top of iteration t
+        int64_t pend_lab = load_label(t);          // row t
+        float2 pend_edge = load_edge(t);           // row t
+        float2 fl_prev = load_flow(t - 1);         // TV stencil
+        float m_near_lane = 0.f, m_disp_lane = 0.f;
+        auto flush_tile = [&](int tile_row) {
+            const unsigned nmax = __reduce_max_sync(FULL, __float_as_uint(m_near_lane));
+            if (lane == 0 && nmax != 0u)
+                atomicMax(reinterpret_cast<unsigned *>(p.tile_disp) + ((int64_t)n * p.tiles_y + tile_row) * p.strips + s, nmax);
+            m_near_lane = 0.f;
+        };
 
 #pragma unroll 1
         for (; t < yb; ++t) {
-            // ---- stage A/B: plan row t+kLD, load flow of row t+kLD+2, aux of row t+kLD+1 ----
-            plan_row(t + kLD, fl[kLD], row_ymin[kLD], row_ymax[kLD]);
-            pend_ymin[kLD] = row_ymin[kLD];
-            const float2 fl_new = load_flow(t + kLD + 2);
-            int64_t lab_new; float2 dc_new;
-            load_aux(t + kLD + 1, lab_new, dc_new);
+            VLG_PROF_START
+            // ---- stage A: take over last iteration's loads, issue this iteration's ----
+            fq[kLD] = pend_fl;
+            const int64_t lb = pend_lab;
+            const float2 fedge = pend_edge;
+            pend_fl = load_flow(t + kLD + 1);
+            pend_lab = load_label(t + 1);
+            pend_edge = load_edge(t + 1);
+            VLG_PROF(7)
+            // ---- stage B: plan row t+kLD ----
+            wtq[kLD] = plan_row(t + kLD, fq[kLD], xyq[kLD], rlq[kLD], min(rlq[0], rlq[1]));
+            VLG_PROF(0)
 
             // ---- stage C: output row t ----
-            const float2 f = fl[0];
-            float mx, my;
-            const float2 xy = source_xy(cc, f, bxv, base_coord(t, cc.Hm1), mx, my);
-            const Taps tp = taps_from_xy(cc, xy, mx, my);
+            const float2 f = fq[0];
             const int y = t;
+            const float2 xy = xyq[0];
+            float mx = mx_c, my = my_c;
+            if (border) {   // the clipped position tells whether the border clip was active
+                mx = (xy.x <= 0.0f || xy.x >= cc.Wm1) ? 0.0f : mx;
+                my = (xy.y <= 0.0f || xy.y >= cc.Hm1) ? 0.0f : my;
+            }
+            const Taps tp = taps_from_xy(cc, xy, mx, my);
 
             // displacement bookkeeping for pass 2 (near radius per tile, far queue)
-            float disp = col_ok ? tap_displacement(cc, tp, y, x) : 0.f;
+            if ((y & (kTH - 1)) == 0 && y != ya) flush_tile(y / kTH - 1);
+            const float disp = col_ok ? tap_displacement(cc, tp, y, x) : 0.f;
             const bool is_far = disp >= (float)VLG_NEAR_RADIUS;
-            {
-                const unsigned dmax = __reduce_max_sync(FULL, __float_as_uint(disp));
-                m_disp = fmaxf(m_disp, __uint_as_float(dmax));
-                const unsigned nmax = __reduce_max_sync(FULL, __float_as_uint(is_far ? 0.f : disp));
-                const int tr = y / kTH;
-                if (tr != tile_row) {
-                    if (tile_row >= 0 && lane == 0 && m_near_tile > 0.f)
-                        atomicMax(reinterpret_cast<unsigned *>(p.tile_disp) + ((int64_t)n * p.tiles_y + tile_row) * p.strips + s,
-                                  __float_as_uint(m_near_tile));
-                    tile_row = tr; m_near_tile = 0.f;
-                }
-                m_near_tile = fmaxf(m_near_tile, __uint_as_float(nmax));
-            }
-            if (is_far && p.d_out_lay != nullptr) {
+            m_disp_lane = fmaxf(m_disp_lane, disp);
+            m_near_lane = fmaxf(m_near_lane, is_far ? 0.f : disp);
+            if (is_far && p.d_out_lay != nullptr && !(VLG_ABL & 8)) {
                 if (p.far_list) {
                     p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = (int)(img + (int64_t)y * W + x);
 #pragma unroll
@@ -265,14 +308,18 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
                     atomicOr(&p.hdr->status, VLG_STATUS_FAR_TAPS);
                 }
             }
+            VLG_PROF(1)
 
-            // wait for the ring rows this output row samples
+            // wait for the ring rows this output row samples (normally exactly one: the row issued kLD iterations ago)
             {
-                const int r0 = max(row_ymin[0], max(lo, top - kLR)), r1 = min(row_ymax[0] + 1, top - 1);
-                for (int r = r0; r <= r1; ++r) wait_slot((r + OFF) % kLR);
+                // rows below want_top were issued >= kLD iterations ago; the next one (issued one iteration ago) is
+                // waited for only when some lane samples a row below the reference lanes
+                const bool deeper = __any_sync(FULL, col_ok && tp.y0 + 2 > wtq[0]);
+                const int need = min(wtq[0] + (deeper ? 1 : 0), top);
+                while (ready < need) wait_next();
             }
+            VLG_PROF(2)
 
-            const int64_t lb = lab[0];
             const bool lab_ok = lb >= 0 && lb < K;
             if (col_ok && !lab_ok && lb != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
             const int il = lab_ok ? (int)lb : 0;
@@ -284,14 +331,23 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
             float zl;
             const T *st0 = nullptr, *st1 = nullptr;   // smem addresses of the nw / sw taps when resident
             {
-                const int res_lo = max(lo, top - kLR);
-                const int sl0 = (tp.y0 + OFF) % kLR, sl1 = (tp.y0 + 1 + OFF) % kLR;
-                const int rx0 = tp.x0 - sm.ox[sl0], rx1 = tp.x0 - sm.ox[sl1];
-                if (tp.y0 >= res_lo && tp.y0 + 1 < top && rx0 >= 0 && rx0 + 1 < kLBW && rx1 >= 0 && rx1 + 1 < kLBW) {
-                    st0 = reinterpret_cast<const T *>(sm.ring[sl0]) + rx0 * K;
-                    st1 = reinterpret_cast<const T *>(sm.ring[sl1]) + rx1 * K;
+                // rows [max(lo, top - kLR), ready) are resident and complete
+                const int d_top = top - tp.y0;        // slot(y0) = slot_top - d_top (mod kLR)
+                if (col_ok && tp.y0 >= lo && d_top <= kLR && tp.y0 + 1 < ready) {
+                    int sl0 = slot_top - d_top;
+                    sl0 = sl0 < 0 ? sl0 + kLR : sl0;
+                    const int sl1 = sl0 + 1 == kLR ? 0 : sl0 + 1;
+                    const unsigned rx0 = (unsigned)(tp.x0 - sm.ox[sl0]), rx1 = (unsigned)(tp.x0 - sm.ox[sl1]);
+                    if (rx0 < (unsigned)(kLBW - 1) && rx1 < (unsigned)(kLBW - 1)) {
+                        st0 = reinterpret_cast<const T *>(sm.ring[sl0]) + rx0 * K;
+                        st1 = reinterpret_cast<const T *>(sm.ring[sl1]) + rx1 * K;
+                    }
                 }
             }
+            VLG_PROF(9)
+#ifdef VLG_LAY_PROFILE
+            prof_acc[13] += __popc(__ballot_sync(FULL, col_ok && st0 == nullptr)); prof_acc[14] += __any_sync(FULL, col_ok && st0 == nullptr); prof_acc[15] += 1;
+#endif
             if (st0) {
                 load_px_smem<T, K>(st0, v);       mul2_bcast<K>(z, v, tp.nw);
                 load_px_smem<T, K>(st0 + K, v);   fma2_bcast<K>(z, v, tp.ne);
@@ -308,6 +364,7 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
             }
             // same FMA chain as z[il], so zl == z[il] bit for bit without indexing registers
             zl = __fmaf_rn(vl[3], tp.se, __fmaf_rn(vl[2], tp.sw, __fmaf_rn(vl[1], tp.ne, __fmul_rn(vl[0], tp.nw))));
+            VLG_PROF(10)
 
             float m = z[0];
 #pragma unroll
@@ -320,22 +377,25 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
             }
             const float L2E = 1.4426950408889634f;
             const float ml2 = m * L2E;
-            float se = 0.f;
+            float se4[4] = {0.f, 0.f, 0.f, 0.f};   // four partial sums: a 20-long dependent FADD chain is a stall
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 z[k] = ex2_approx(fmaf(z[k], L2E, -ml2));
-                se += z[k];
+                se4[k & 3] += z[k];
             }
+            const float se = (se4[0] + se4[1]) + (se4[2] + se4[3]);
             if (lab_ok && col_ok) s_ce += wl * (fmaf(lg2_approx(se), 0.6931471805599453f, m) - zl);
+            VLG_PROF(3)
 
             float gix = 0.f, giy = 0.f;
             if (GRAD) {
-                const float cce = (lab_ok && col_ok) ? p.w_ce_over_scale * wl / denom : 0.0f;
-                const float inv = cce / se;
+                const float cce = (lab_ok && col_ok) ? ce_unit * wl : 0.0f;
+                const float inv = cce * rcp_approx(se);
                 mul2_bcast<K>(z, z, inv);
                 const float gl = fmaf(ex2_approx(fmaf(zl, L2E, -ml2)), inv, -cce);
                 m_grad = fmaxf(m_grad, cce);
                 float dnw, dne, dsw, dse;
+                if (VLG_ABL & 4) { dnw = dne = dsw = dse = 0.f; gix = z[3]; giy = z[7]; } else
                 if (st0) {
                     load_px_smem<T, K>(st0, v);       dnw = dot2<K>(z, v);
                     load_px_smem<T, K>(st0 + K, v);   dne = dot2<K>(z, v);
@@ -353,82 +413,65 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
                     for (int k = 0; k < K; ++k) gfull[k] = z[k] - (k == il ? cce : 0.0f);
                     coord_grad_px<T, K>(src_lay, cc, tp, gfull, gix, giy);
                 }
-                if (p.d_out_lay) {
+                VLG_PROF(4)
+                if (p.d_out_lay && !(VLG_ABL & 1)) {
                     // one contiguous row of d(loss)/d(warped layout) leaves through shared memory
                     if (lane == 0) bulk_store_wait_read();        // the previous row's bulk store has read obuf
                     __syncwarp();
+                    VLG_PROF(12)
                     float *ob = sm.obuf + lane * K;
 #pragma unroll
                     for (int k = 0; k < K; k += 4) *reinterpret_cast<float4 *>(ob + k) = make_float4(z[k], z[k + 1], z[k + 2], z[k + 3]);
                     if (lab_ok) ob[il] = gl;
+                    VLG_PROF(11)
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0)
                         bulk_store(p.d_out_lay + (img + (int64_t)y * W + (int64_t)s * kLW) * K, sm.obuf, (unsigned)(npx * K * 4));
                 }
             }
+            VLG_PROF(5)
 
-            // ---- coordinate gradient: rgb part (prefetched) + layout part + TV ----
-            float gx = fmaf(tp.mx, gix, dcp[0].x), gy = fmaf(tp.my, giy, dcp[0].y);
-            if (p.do_tv) {
-                // horizontal neighbours by shuffle; the strip's edge lanes read them from memory
+            // ---- coordinate gradient: layout part + TV (the rgb strip kernel adds its part afterwards) ----
+            float gx = tp.mx * gix, gy = tp.my * giy;
+            if (p.do_tv && !(VLG_ABL & 2)) {
+                // horizontal neighbours by shuffle; the strip's edge lanes carry theirs in the prefetch pipeline
                 float2 fr, flf;
                 fr.x = __shfl_down_sync(FULL, f.x, 1); fr.y = __shfl_down_sync(FULL, f.y, 1);
                 flf.x = __shfl_up_sync(FULL, f.x, 1);  flf.y = __shfl_up_sync(FULL, f.y, 1);
-                if (lane == 31 && x + 1 < W) fr = __ldg(coords + (y * W + x + 1));
-                if (lane == 0 && x >= 1) flf = __ldg(coords + (y * W + x - 1));
-                if (col_ok) {
-                    if (y + 1 < H) {
-                        const float2 df = make_float2(fl[1].x - f.x, fl[1].y - f.y);
-                        s_tvh += fabsf(df.x) + fabsf(df.y);
-                        gx -= signed_c1(p.c_tvh, df.x);
-                        gy -= signed_c1(p.c_tvh, df.y);
-                    }
-                    if (y >= 1) {
-                        gx += signed_c1(p.c_tvh, f.x - fl_prev.x);
-                        gy += signed_c1(p.c_tvh, f.y - fl_prev.y);
-                    }
-                    if (x + 1 < W) {
-                        const float2 df = make_float2(fr.x - f.x, fr.y - f.y);
-                        s_tvw += fabsf(df.x) + fabsf(df.y);
-                        gx -= signed_c1(p.c_tvw, df.x);
-                        gy -= signed_c1(p.c_tvw, df.y);
-                    }
-                    if (x >= 1) {
-                        gx += signed_c1(p.c_tvw, f.x - flf.x);
-                        gy += signed_c1(p.c_tvw, f.y - flf.y);
-                    }
-                }
+                if (lane == 31) fr = fedge;
+                if (lane == 0) flf = fedge;
+                const bool has_dn = y + 1 < H, has_up = y >= 1;      // warp-uniform
+                const float cD = has_dn ? cV : 0.f, cU = has_up ? cV : 0.f;
+                const float2 dd = make_float2(fq[1].x - f.x, fq[1].y - f.y), du = make_float2(f.x - fl_prev.x, f.y - fl_prev.y);
+                const float2 dr = make_float2(fr.x - f.x, fr.y - f.y), dl = make_float2(f.x - flf.x, f.y - flf.y);
+                s_tvh = fmaf(fabsf(dd.x) + fabsf(dd.y), has_dn ? mCol : 0.f, s_tvh);
+                s_tvw = fmaf(fabsf(dr.x) + fabsf(dr.y), mRt, s_tvw);
+                gx += (signed_c1(cU, du.x) - signed_c1(cD, dd.x)) + (signed_c1(cL, dl.x) - signed_c1(cR, dr.x));
+                gy += (signed_c1(cU, du.y) - signed_c1(cD, dd.y)) + (signed_c1(cL, dl.y) - signed_c1(cR, dr.y));
             }
-            if (GRAD && p.d_coords && col_ok)
+            if (GRAD && p.d_coords && col_ok && !(VLG_ABL & 16))
                 reinterpret_cast<float2 *>(p.d_coords)[img + (int64_t)y * W + x] = make_float2(gx, gy);
+            VLG_PROF(6)
 
-            // ---- slide the pipeline ----
+            // ---- slide the pipelines of COMPUTED values (moves of landed data are harmless) ----
             fl_prev = f;
 #pragma unroll
-            for (int i = 0; i < kLD + 1; ++i) fl[i] = fl[i + 1];
-            fl[kLD + 1] = fl_new;
-#pragma unroll
-            for (int i = 0; i < kLD; ++i) {
-                lab[i] = lab[i + 1]; dcp[i] = dcp[i + 1];
-                row_ymin[i] = row_ymin[i + 1]; row_ymax[i] = row_ymax[i + 1]; pend_ymin[i] = pend_ymin[i + 1];
-            }
-            lab[kLD] = lab_new; dcp[kLD] = dc_new;
+            for (int i = 0; i < kLD; ++i) { fq[i] = fq[i + 1]; xyq[i] = xyq[i + 1]; wtq[i] = wtq[i + 1]; rlq[i] = rlq[i + 1]; }
         }
-        if (tile_row >= 0 && lane == 0 && m_near_tile > 0.f)
-            atomicMax(reinterpret_cast<unsigned *>(p.tile_disp) + ((int64_t)n * p.tiles_y + tile_row) * p.strips + s,
-                      __float_as_uint(m_near_tile));
-#pragma unroll
-        for (int sl = 0; sl < kLR; ++sl)
-            if ((in_flight >> sl) & 1u) wait_slot(sl);
+        flush_tile((yb - 1) / kTH);
+        m_disp = fmaxf(m_disp, m_disp_lane);
+        while (ready < top) wait_next();      // nothing may be in flight when the ring is restarted or released
     }
     if (GRAD && p.d_out_lay && lane == 0) bulk_store_wait_read();
 
+    VLG_PROF_FLUSH
     // ---- per-warp partial sums ----
     s_ce = warp_sum(s_ce);
     s_tvh = warp_sum(s_tvh);
     s_tvw = warp_sum(s_tvw);
     m_grad = warp_max(m_grad);
+    m_disp = warp_max(m_disp);
     if (lane == 0) {
         reinterpret_cast<float4 *>(p.partials)[gw] = make_float4(s_ce, s_tvh, s_tvw, 0.f);
         if (m_disp > 0.f) atomicMax(&p.hdr->maxdisp_bits, __float_as_uint(m_disp));
