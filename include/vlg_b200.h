@@ -51,7 +51,9 @@ extern "C" {
 #define VLG_FLAG_NO_FAR_PATH 1u /* caller asserts |displacement| < VLG_NEAR_RADIUS; far taps raise status */
 #define VLG_FLAG_NO_TMA 2u      /* stage the source-layout window with cp.async instead of a TMA tensor map   */
 #define VLG_FLAG_TILE_RGB 4u    /* evaluate the rgb terms in the tile kernel instead of the column-strip kernel */
-#define VLG_FLAG_TILE_LAYOUT 8u /* evaluate the layout terms in the tile kernel instead of the row-ring strip kernel */
+#define VLG_FLAG_TILE_LAYOUT 8u /* evaluate the layout terms in the first (non-persistent) tile kernel            */
+#define VLG_FLAG_STRIP_LAYOUT 16u /* evaluate the layout terms in the per-warp row-ring strip kernel instead of the
+                                   * persistent double-buffered tile kernel                                          */
 
 /* term_mask bits */
 #define VLG_TERM_L1 1u

@@ -11,6 +11,7 @@
 #include "vlg_pass2.cuh"
 #include "vlg_rgb.cuh"
 #include "vlg_lay.cuh"
+#include "vlg_laytile.cuh"
 
 using namespace vlg;
 
@@ -454,6 +455,38 @@ static int launch_lay(LayParams lp, const CUtensorMap &map, bool grad, cudaStrea
     return check_launch("lay_strip_kernel");
 }
 
+// Persistent launch of the double-buffered layout tile kernel: one wave of resident CTAs.
+template <int K>
+static int launch_laytile(const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
+    const size_t smem = sizeof(LayTileSmem<K>);
+    static int ctas_resident = 0;
+    if (!ctas_resident) {
+        cudaError_t e = cudaFuncSetAttribute(lay_tile_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lay_tile_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int dev = 0, sms = 0, per_sm = 0;
+        if (e == cudaSuccess) e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lay_tile_kernel<K, true>, kThreads, smem);
+        if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "lay_tile_kernel setup: %s", cudaGetErrorString(e));
+        ctas_resident = sms * per_sm;
+    }
+    const int64_t n_tiles = (int64_t)lp.N * lp.strips * lp.tiles_y;
+    int64_t blocks = ctas_resident < kLayMaxWarps ? ctas_resident : kLayMaxWarps;
+    if (blocks * 2 > n_tiles) blocks = (n_tiles + 1) / 2;    // at least two tiles per CTA keeps the pipeline meaningful
+    if (blocks < 1) blocks = 1;
+    if (grad) lay_tile_kernel<K, true><<<(unsigned)blocks, kThreads, smem, st>>>(lp, map);
+    else lay_tile_kernel<K, false><<<(unsigned)blocks, kThreads, smem, st>>>(lp, map);
+    return check_launch("lay_tile_kernel");
+}
+
+static int dispatch_laytile(const vlg_problem_t *prob, const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
+#define X(k) if constexpr ((k) % 4 == 0) { if (prob->K == k) return launch_laytile<k>(lp, map, grad, st); }
+    VLG_FOR_EACH_K(X)
+#undef X
+    return fail(VLG_ERR_UNSUPPORTED, "layout tile kernel: K not compiled in");
+}
+
 static int dispatch_lay(const vlg_problem_t *prob, const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
 #define X(k) if constexpr ((k) % 4 == 0) { if (prob->K == k) return launch_lay<k>(lp, map, grad, st); }
     VLG_FOR_EACH_K(X)
@@ -537,7 +570,8 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     bool lay_done = false;
     if (warp && has_lay && prob->dtype == VLG_F32 && prob->K % 4 == 0 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_TILE_LAYOUT))) {
         CUtensorMap row_map;
-        if (make_layout_map(prob, src_layout, &row_map, kLBW, 1)) {
+        const bool strips = (prob->flags & VLG_FLAG_STRIP_LAYOUT) != 0;
+        if (strips ? make_layout_map(prob, src_layout, &row_map, kLBW, 1) : make_layout_map(prob, src_layout, &row_map, kTSW, kTSH)) {
             LayParams lp{};
             lp.cc = pp.cc;
             lp.N = pp.N; lp.strips = pp.tiles_x; lp.tiles_y = pp.tiles_y;
@@ -552,7 +586,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.partials = (float *)(ws + L.partials_lay);
             lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
             lp.red = pp.red; lp.hdr = hdr;
-            rc = dispatch_lay(prob, lp, row_map, need_grad, st);
+            rc = strips ? dispatch_lay(prob, lp, row_map, need_grad, st) : dispatch_laytile(prob, lp, row_map, need_grad, st);
             if (rc) return rc;
             lay_done = true;
         }
