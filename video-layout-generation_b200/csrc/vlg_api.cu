@@ -115,6 +115,16 @@ __global__ void count_valid_kernel(const int64_t *__restrict__ label, int64_t P,
     __syncthreads();
     unsigned int cnt = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (!class_weight && (reinterpret_cast<uintptr_t>(label) & 15) == 0) {
+        // unweighted: two labels per 128-bit load, four loads in flight per thread
+        const longlong2 *l2 = reinterpret_cast<const longlong2 *>(label);
+        const int64_t P2 = P >> 1;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P2; i += stride) {
+            const longlong2 v = __ldg(l2 + i);
+            cnt += (v.x != ignore_index) + (v.y != ignore_index);
+        }
+        if ((P & 1) && blockIdx.x == 0 && threadIdx.x == 0) cnt += __ldg(label + P - 1) != ignore_index;
+    } else
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
         const int64_t l = __ldg(label + i);
         cnt += l != ignore_index;
@@ -505,8 +515,9 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "memset header: %s", cudaGetErrorString(e));
     const int64_t P = prob->N * prob->H * prob->W;
     const bool has_lay = src_layout && tgt_label;
+    const bool rgb_strips = warp && src_rgb && tgt_rgb && !(prob->flags & VLG_FLAG_TILE_RGB);
     if (has_lay) {
-        const int blocks = (int)((P + 256 * 8 - 1) / (256 * 8));
+        const int blocks = (int)((P + 256 * 16 - 1) / (256 * 16));
         count_valid_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(tgt_label, P, prob->ignore_index, (int)prob->K,
                                                                      prob->ce_class_weight, hdr);
         int rc = check_launch("count_valid_kernel");
@@ -543,12 +554,11 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
     pp.hdr = hdr;
     pp.flags = prob->flags;
-    // The rgb terms run in the column-strip kernel, launched AFTER the kernel that owns the layout / TV
-    // terms: that one stores its part of d(loss)/d(coords), the strip kernel adds the rgb part (loaded a
-    // row ahead) and, being last, performs the final reduction of every partial sum.
-    const bool rgb_strips = warp && src_rgb && tgt_rgb && !(prob->flags & VLG_FLAG_TILE_RGB);
-    RgbParams rp{};
+    // The rgb terms run in the column-strip kernel, launched BEFORE the kernel that owns the layout / TV
+    // terms: it stores its part of d(loss)/d(coords) (and the label count); the layout kernel, which has
+    // issue slots to spare, loads that part one tile ahead, adds its own and performs the final reduction.
     if (rgb_strips) {
+        RgbParams rp{};
         rp.cc = pp.cc;
         rp.N = (int)prob->N;
         rp.strips = (int)((prob->W + kRS - 1) / kRS);
@@ -562,9 +572,10 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
         rp.d_out_rgb = need_grad ? (float *)d_out_rgb : nullptr;
         rp.partials = (float *)(ws + L.partials_rgb);
         rp.hdr = hdr;
-        rp.red = pp.red;
-        pp.red.out = nullptr;
+        int rc0 = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
+        if (rc0) return rc0;
         pp.src_rgb = nullptr; pp.tgt_rgb = nullptr; pp.d_out_rgb = nullptr;
+        pp.accum_dcoords = 1;
     }
     int rc = VLG_OK;
     bool lay_done = false;
@@ -580,6 +591,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.class_weight = pp.class_weight; lp.weighted_denom = pp.weighted_denom;
             lp.w_ce_over_scale = pp.w_ce_over_scale;
             lp.c_tvh = pp.c_tvh; lp.c_tvw = pp.c_tvw; lp.do_tv = pp.do_tv;
+            lp.accum_dcoords = pp.accum_dcoords;
             lp.d_coords = need_grad ? d_coords : nullptr;
             lp.d_out_lay = need_grad ? (float *)d_out_lay : nullptr;
             lp.out_argmax = out_argmax;
@@ -598,7 +610,6 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
         rc = dispatch_pass1(prob, warp, pp, lay_map, L.n_blocks, st);
         if (rc) return rc;
     }
-    if (rgb_strips) rc = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
     return rc;
 }
 

@@ -73,6 +73,7 @@ struct LayParams {
     float w_ce_over_scale;
     float c_tvh, c_tvw;
     int do_tv;
+    int accum_dcoords;             // d_coords already holds the rgb part (the rgb strip kernel ran before): add to it
     float *d_coords;               // nullable (validation)
     float *d_out_lay;              // [P][K] fp32 staging, nullable
     int64_t *out_argmax;           // nullable
@@ -252,6 +253,11 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
         float2 pend_fl = load_flow(t + kLD);       // row t+kLD: planned at the top of iteration t
         int64_t pend_lab = load_label(t);          // row t
         float2 pend_edge = load_edge(t);           // row t
+        auto load_dc = [&](int r) -> float2 {      // rgb part of d(loss)/d(coords) of row r
+            return (GRAD && p.accum_dcoords && col_ok && r < yb)
+                       ? __ldcg(reinterpret_cast<const float2 *>(p.d_coords) + img + (r * W + x)) : make_float2(0.f, 0.f);
+        };
+        float2 pend_dc = load_dc(t);               // row t
         float2 fl_prev = load_flow(t - 1);         // TV stencil
         float m_near_lane = 0.f, m_disp_lane = 0.f;
         auto flush_tile = [&](int tile_row) {
@@ -268,6 +274,8 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
             fq[kLD] = pend_fl;
             const int64_t lb = pend_lab;
             const float2 fedge = pend_edge;
+            const float2 dc = pend_dc;
+            pend_dc = load_dc(t + 1);
             pend_fl = load_flow(t + kLD + 1);
             pend_lab = load_label(t + 1);
             pend_edge = load_edge(t + 1);
@@ -432,8 +440,8 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
             }
             VLG_PROF(5)
 
-            // ---- coordinate gradient: layout part + TV (the rgb strip kernel adds its part afterwards) ----
-            float gx = tp.mx * gix, gy = tp.my * giy;
+            // ---- coordinate gradient: rgb part (prefetched) + layout part + TV ----
+            float gx = fmaf(tp.mx, gix, dc.x), gy = fmaf(tp.my, giy, dc.y);
             if (p.do_tv && !(VLG_ABL & 2)) {
                 // horizontal neighbours by shuffle; the strip's edge lanes carry theirs in the prefetch pipeline
                 float2 fr, flf;

@@ -164,6 +164,13 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
     __syncthreads();
     float2 pend_f = load_coords(2, g2), pend_h = load_halo(2, g2);
     int64_t pend_lab = load_label(0, g0);
+    // rgb part of d(loss)/d(coords), written by the rgb strip kernel that ran before: loaded one tile ahead
+    auto load_dc = [&](int i, const TileGeo &g) -> float2 {
+        const int y = g.ty0 + wid, x = g.tx0 + lane;
+        return (GRAD && p.accum_dcoords && i < nt && y < H && x < W)
+                   ? __ldcg(reinterpret_cast<const float2 *>(p.d_coords) + ((int64_t)g.n * H * W + (int64_t)y * W + x)) : make_float2(0.f, 0.f);
+    };
+    float2 pend_dc = load_dc(0, g0);
 
 #pragma unroll 1
     for (int i = 0; i < nt; ++i) {
@@ -171,6 +178,8 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         // ---- take over last iteration's loads, issue this iteration's ----
         const float2 f2 = pend_f, h2 = pend_h;
         const int64_t lb = pend_lab;
+        const float2 dc = pend_dc;
+        pend_dc = load_dc(i + 1, g1);
         pend_f = load_coords(i + 3, g3);
         pend_h = load_halo(i + 3, g3);
         pend_lab = load_label(i + 1, g1);
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         }
 
         // ---- coordinate gradient: layout part + TV ----
-        float gx = tp.mx * gix, gy = tp.my * giy;
+        float gx = fmaf(tp.mx, gix, dc.x), gy = fmaf(tp.my, giy, dc.y);
         if (p.do_tv) {
             const float2 *fc = &sm.flow[b][(wid + 1) * kFW + lane + 1];
             const float2 f = f0, fdn = fc[kFW], fup = fc[-kFW], frt = fc[1], flt = fc[-1];

@@ -59,6 +59,7 @@ struct Pass1Params {
     WsHeader *hdr;
     uint32_t flags;
     int use_tma;            // the layout window is staged by one cp.async.bulk.tensor per CTA
+    int accum_dcoords;      // d_coords already holds the rgb part (written by rgb_strip_kernel): add to it
 };
 
 #ifndef VLG_P1_MIN_BLOCKS
@@ -223,8 +224,11 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
     // hidden behind phases 0-1 instead of stalling the longest phase.
     int64_t lab_pre = 0;
     float denom_pre = 1.0f, wl_pre = 1.0f;
+    float2 dc_pre = make_float2(0.f, 0.f);
     {
         const int py = ty0 + tid / kTW, px = tx0 + (tid & (kTW - 1));
+        if (WARP && p.accum_dcoords && p.need_grad && p.d_coords && py < H && px < W)
+            dc_pre = __ldcg(reinterpret_cast<const float2 *>(p.d_coords) + img_px + (int64_t)py * W + px);
         if (has_lay && py < H && px < W) {
             lab_pre = __ldg(p.label + img_px + (int64_t)py * W + px);
             if (p.class_weight && lab_pre >= 0 && lab_pre < K) wl_pre = __ldg(p.class_weight + lab_pre);
@@ -691,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         }
 
         if (WARP) {
-            float gx = t.mx * gix, gy = t.my * giy;
+            float gx = fmaf(t.mx, gix, dc_pre.x), gy = fmaf(t.my, giy, dc_pre.y);
             if (p.do_tv) {
                 const float2 f = VLG_FLOW_AT(0, 0);
                 if (y + 1 < H) {

@@ -46,11 +46,10 @@ struct RgbParams {
     const float *coords;
     float c_l1, c_gd, c_ssim;       // gradient scales (0 when the term is masked off)
     uint32_t terms;
-    float *d_coords;                // [P][2] d(loss)/d(coords): holds the layout + TV part, the rgb part is ADDED (nullable)
+    float *d_coords;                // [P][2] rgb part of d(loss)/d(coords); the layout kernel that follows adds its own (nullable)
     float *d_out_rgb;               // [P][3] fp32 staging for pass 2 (nullable)
     float *partials;                // [n_warps][kRgbSlots]
     WsHeader *hdr;
-    ReduceParams red;               // red.out != NULL: the last CTA performs the final reduction
 };
 
 struct RgbRow {                     // one row in flight: raw taps, target, weights
@@ -106,6 +105,7 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
     const unsigned FULL = 0xffffffffu;
 
     float s_l1 = 0.f, s_gd = 0.f, s_ssim = 0.f, m_grad = 0.f;
+
     const float inv9 = 1.0f / 9.0f, C1 = 1e-4f, C2 = 9e-4f;
     const float kk = -p.c_ssim * (2.0f / 9.0f);
 
@@ -153,13 +153,6 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
             return (t >= 0 && t < H && t <= t_last) ? __ldg(coords + (t * W + xc)) : make_float2(0.f, 0.f);
         };
 
-        // the layout / TV part of d_coords of the row finalised NEXT iteration (row t-1), loaded one iteration ahead
-        auto load_dc = [&](int r) -> float2 {
-            return (GRAD && p.d_coords && out_lane && r >= ya && r < yb)
-                       ? __ldcg(reinterpret_cast<const float2 *>(p.d_coords) + img + (r * W + x)) : make_float2(0.f, 0.f);
-        };
-        float2 dc_next = make_float2(0.f, 0.f);
-
         int t = ya - 2;
         float2 fl_next = load_flow(t + 1);
         RgbRow cur;
@@ -169,8 +162,6 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
         for (; t <= t_last; ++t) {
             // ---- software pipeline: flow of row t+2, taps + target of row t+1 ----
             const float2 fl_next2 = load_flow(t + 2);
-            const float2 dc_use = dc_next;       // loaded during the previous iteration: row t-2
-            dc_next = load_dc(t - 1);
             RgbRow nxt;
             rgb_issue_row<T>(nxt, cc, fl_next, bxv, t + 1, xc, src, tgt, t + 1 >= 0 && t + 1 < H && t + 1 <= t_last);
 
@@ -270,7 +261,7 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
             // ---- gradient of row t-2 is complete ----
             if (GRAD && own2) {
                 float dr[3];
-                float gx = dc_use.x, gy = dc_use.y;
+                float gx = 0.f, gy = 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float sA = (QA2[c] + QA1[c]) + QA0[c], sB = (QB2[c] + QB1[c]) + QB0[c];
@@ -317,21 +308,8 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
         reinterpret_cast<float4 *>(p.partials)[gw] = o;
         if (m_grad > 0.f) atomicMax(&p.hdr->maxgrad_bits, __float_as_uint(m_grad));
         if (gw == 0) p.hdr->n_rgb = gridDim.x * (kRgbThreads / 32);
-        __threadfence();
     }
 
-    // ---- the last CTA to finish reduces every partial row (fixed order) ----
-    if (p.red.out != nullptr) {
-        __shared__ double s_red[6 * kRgbThreads];
-        __shared__ int s_last;
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&p.hdr->blocks_done, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            reduce_partials_block<kRgbThreads>(p.red, s_red);
-        }
-    }
 }
 
 }  // namespace vlg
