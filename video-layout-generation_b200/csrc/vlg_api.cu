@@ -420,7 +420,7 @@ static int launch_rgb(RgbParams rp, bool grad, cudaStream_t st) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgb_strip_kernel<T, true>, kRgbThreads, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgb_strip_kernel<T, true, false>, kRgbThreads, 0);
         if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "rgb_strip_kernel occupancy query: %s", cudaGetErrorString(e));
         warps_resident = sms * per_sm * (kRgbThreads / 32);
     }
@@ -429,8 +429,11 @@ static int launch_rgb(RgbParams rp, bool grad, cudaStream_t st) {
     if (warps * min_rows > rp.total_rows) warps = (rp.total_rows + min_rows - 1) / min_rows;
     const int64_t blocks = (warps + kRgbThreads / 32 - 1) / (kRgbThreads / 32);
     rp.chunk = (rp.total_rows + blocks * (kRgbThreads / 32) - 1) / (blocks * (kRgbThreads / 32));
-    if (grad) rgb_strip_kernel<T, true><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
-    else rgb_strip_kernel<T, false><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
+    const bool brd = rp.cc.padding == VLG_PAD_BORDER;
+    if (grad && brd) rgb_strip_kernel<T, true, true><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
+    else if (grad) rgb_strip_kernel<T, true, false><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
+    else if (brd) rgb_strip_kernel<T, false, true><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
+    else rgb_strip_kernel<T, false, false><<<(unsigned)blocks, kRgbThreads, 0, st>>>(rp);
     return check_launch("rgb_strip_kernel");
 }
 

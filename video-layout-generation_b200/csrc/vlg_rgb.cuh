@@ -59,7 +59,10 @@ struct RgbRow {                     // one row in flight: raw taps, target, weig
     unsigned tin;                   // bit k: tap k lies inside the image
 };
 
-template <typename T>
+// BORDER: taps are clamped into the image, so the only out-of-image tap is x0+1 == W (or y0+1 == H) and it
+// carries weight exactly 0 and a coordinate-gradient mask of exactly 0: the clamped load stands in for
+// the zero torch substitutes and no per-tap select is needed (finite inputs).
+template <typename T, bool BORDER>
 __device__ __forceinline__ void rgb_issue_row(RgbRow &r, const CoordCfg &cc, float2 fl, float bxv, int t, int xc,
                                               const T *__restrict__ src, const T *__restrict__ tgt, bool row_ok) {
     const int H = cc.H, W = cc.W;
@@ -74,10 +77,14 @@ __device__ __forceinline__ void rgb_issue_row(RgbRow &r, const CoordCfg &cc, flo
         load_px<T, 3>(src + (int64_t)(y1c * W + x0c) * 3, r.v[2]);
         load_px<T, 3>(src + (int64_t)(y1c * W + x1c) * 3, r.v[3]);
         load_px<T, 3>(tgt + (int64_t)(t * W + xc) * 3, r.b);
-        const bool xin0 = tp.x0 >= 0 && tp.x0 < W, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < W;
-        const bool yin0 = tp.y0 >= 0 && tp.y0 < H, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < H;
-        r.tin = (unsigned)(yin0 && xin0) | ((unsigned)(yin0 && xin1) << 1) | ((unsigned)(yin1 && xin0) << 2) |
-                ((unsigned)(yin1 && xin1) << 3);
+        if (!BORDER) {
+            const bool xin0 = tp.x0 >= 0 && tp.x0 < W, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < W;
+            const bool yin0 = tp.y0 >= 0 && tp.y0 < H, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < H;
+            r.tin = (unsigned)(yin0 && xin0) | ((unsigned)(yin0 && xin1) << 1) | ((unsigned)(yin1 && xin0) << 2) |
+                    ((unsigned)(yin1 && xin1) << 3);
+        } else {
+            r.tin = 15u;
+        }
         r.nw = tp.nw; r.ne = tp.ne; r.sw = tp.sw; r.se = tp.se;
         r.wx1 = tp.ix - tp.fx0; r.wy1 = tp.iy - tp.fy0;
         r.mx = mx; r.my = my;
@@ -93,7 +100,7 @@ __device__ __forceinline__ void rgb_issue_row(RgbRow &r, const CoordCfg &cc, flo
     }
 }
 
-template <typename T, bool GRAD>
+template <typename T, bool GRAD, bool BORDER>
 __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_kernel(const RgbParams p) {
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
@@ -123,7 +130,6 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
         const int xc = min(max(x, 0), W - 1);
         const float bxv = base_coord(xc, cc.Wm1);
         const float cR = (col_ok && x + 1 < W) ? p.c_gd : 0.f;      // pair (x, x+1) exists
-        const float cL = (col_ok && x >= 1) ? p.c_gd : 0.f;         // pair (x-1, x) exists
         const float cV = col_ok ? p.c_gd : 0.f;
         const float mR = (out_lane && x + 1 < W) ? 1.f : 0.f;       // this lane counts the pair (x, x+1)
         const bool win_x = x >= 1 && x <= W - 2;                    // a 3x3 window can be centred on column x
@@ -156,14 +162,14 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
         int t = ya - 2;
         float2 fl_next = load_flow(t + 1);
         RgbRow cur;
-        rgb_issue_row<T>(cur, cc, load_flow(t), bxv, t, xc, src, tgt, t >= 0 && t < H);
+        rgb_issue_row<T, BORDER>(cur, cc, load_flow(t), bxv, t, xc, src, tgt, t >= 0 && t < H);
 
 #pragma unroll 1
         for (; t <= t_last; ++t) {
             // ---- software pipeline: flow of row t+2, taps + target of row t+1 ----
             const float2 fl_next2 = load_flow(t + 2);
             RgbRow nxt;
-            rgb_issue_row<T>(nxt, cc, fl_next, bxv, t + 1, xc, src, tgt, t + 1 >= 0 && t + 1 < H && t + 1 <= t_last);
+            rgb_issue_row<T, BORDER>(nxt, cc, fl_next, bxv, t + 1, xc, src, tgt, t + 1 >= 0 && t + 1 < H && t + 1 <= t_last);
 
             // ---- row t ----
             const bool row_ok = t >= 0 && t < H;
@@ -174,6 +180,7 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
             const float mo0 = (own0 && out_lane) ? 1.f : 0.f, mo1 = (own1 && out_lane) ? 1.f : 0.f;
             const float mR0 = own0 ? mR : 0.f;
             const bool winv = win_x && win_y;
+            const float mw1 = winv ? mo1 : 0.f;       // this lane counts the window centred on (x, t-1)
 
             float a0[3], b0[3], G0[3], Dx0[3], Dy0[3];
             float QA0[3], QB0[3], QC0[3];
@@ -183,8 +190,8 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                 const float wx1 = cur.wx1, wy1 = cur.wy1, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float v0 = (cur.tin & 1u) ? cur.v[0][c] : 0.f, v1 = (cur.tin & 2u) ? cur.v[1][c] : 0.f;
-                    const float v2 = (cur.tin & 4u) ? cur.v[2][c] : 0.f, v3 = (cur.tin & 8u) ? cur.v[3][c] : 0.f;
+                    const float v0 = (BORDER || (cur.tin & 1u)) ? cur.v[0][c] : 0.f, v1 = (BORDER || (cur.tin & 2u)) ? cur.v[1][c] : 0.f;
+                    const float v2 = (BORDER || (cur.tin & 4u)) ? cur.v[2][c] : 0.f, v3 = (BORDER || (cur.tin & 8u)) ? cur.v[3][c] : 0.f;
                     float acc = __fmul_rn(v0, cur.nw);
                     acc = __fmaf_rn(v1, cur.ne, acc);
                     acc = __fmaf_rn(v2, cur.sw, acc);
@@ -208,12 +215,11 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                 s_l1 = fmaf(fabsf(d), mo0, s_l1);
                 float g = signed_c1(p.c_l1, d);
                 // GD along W (reference `yloss`, src/loss.py:23-24): pairs (x, x+1) and (x-1, x)
-                {
+                {   // each lane evaluates its pair (x, x+1) once; the right neighbour receives the gradient by a shuffle
                     const float da = ar - a, tt = fabsf(da) - fabsf(br - b);
                     s_gd = fmaf(fabsf(tt), mR0, s_gd);
-                    g -= signed_c(cR, tt, da);
-                    const float dl = a - al, tl = fabsf(dl) - fabsf(b - bl);
-                    g += signed_c(cL, tl, dl);
+                    const float gr = signed_c(cR, tt, da);
+                    g += __shfl_up_sync(FULL, gr, 1) - gr;
                 }
                 // GD along H (reference `xloss`, src/loss.py:21-22): pair (t-1, t), counted by the owner of row t-1
                 if (vpair) {
@@ -245,13 +251,13 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                 const float r = inv_d1 * inv_d2;
                 const float S = (n1 * n2) * r;
                 const float v = fmaf(-0.5f, S, 0.5f);
-                s_ssim = fmaf(winv ? __saturatef(v) : 0.f, mo1, s_ssim);
+                s_ssim = fmaf(__saturatef(v), mw1, s_ssim);
                 if (GRAD) {
                     // dS/dx_p = A + B x_p + C y_p; the clamp passes gradient on [0, 1]
-                    const bool on = winv && v >= 0.0f && v <= 1.0f;
-                    const float kA = on ? kk * (m2.y * (n2 - n1) * r + S * m2.x * (inv_d2 - inv_d1)) : 0.f;
-                    const float kB = on ? kk * (-S * inv_d2) : 0.f;
-                    const float kC = on ? kk * (n1 * r) : 0.f;
+                    const float kke = (winv && v >= 0.0f && v <= 1.0f) ? kk : 0.f;
+                    const float kA = kke * (m2.y * (n2 - n1) * r + S * m2.x * (inv_d2 - inv_d1));
+                    const float kB = kke * (-S * inv_d2);
+                    const float kC = kke * (n1 * r);
                     QA0[c] = (__shfl_up_sync(FULL, kA, 1) + kA) + __shfl_down_sync(FULL, kA, 1);
                     QB0[c] = (__shfl_up_sync(FULL, kB, 1) + kB) + __shfl_down_sync(FULL, kB, 1);
                     QC0[c] = (__shfl_up_sync(FULL, kC, 1) + kC) + __shfl_down_sync(FULL, kC, 1);

@@ -39,7 +39,9 @@ class WarpLossConfig:
     global_batch: int = 0                 # data-parallel: divisor batch (0 = local batch)
     assume_near: bool = False             # caller asserts |flow| < NEAR_RADIUS: skip far-path launches
     use_tma: bool = True                  # stage source layout rows / windows with TMA tensor maps when possible
-    tile_kernels: bool = False            # evaluate pass 1 in the 32x8 tile kernel instead of the per-warp strip kernels
+    tile_kernels: bool = False            # evaluate ALL of pass 1 in the first (non-persistent) 32x8 tile kernel
+    layout_kernel: str = "tile2"          # layout half of pass 1: 'tile2' persistent double-buffered tile kernel (default),
+                                          # 'strip' per-warp TMA row ring, 'tile' first tile kernel
     term_mask: int = 0                    # 0 = all terms
     class_weight: Optional[torch.Tensor] = None   # per-class CE weights (K floats on the device)
     ce_norm: str = "torch"                # 'torch' (weighted mean) | 'count' (sum / n_known, src/models/simple.py:56-59)
@@ -105,6 +107,9 @@ def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
     flags = (_cabi.FLAG_NO_FAR_PATH if cfg.assume_near else 0) | (0 if cfg.use_tma else _cabi.FLAG_NO_TMA)
     if cfg.tile_kernels:
         flags |= _cabi.FLAG_TILE_RGB | _cabi.FLAG_TILE_LAYOUT
+    if cfg.layout_kernel not in ("tile2", "strip", "tile"):
+        raise VlgError(f"layout_kernel must be 'tile2', 'strip' or 'tile', not {cfg.layout_kernel!r}")
+    flags |= {"tile2": 0, "strip": _cabi.FLAG_STRIP_LAYOUT, "tile": _cabi.FLAG_TILE_LAYOUT}[cfg.layout_kernel]
     return Problem(N=N, H=H, W=W, K=K, dtype=_DTYPES[dtype], padding=_PADDING[cfg.padding_mode],
                    coord_mode=_cabi.COORD_GRID if cfg.coords_are_grid else _cabi.COORD_FLOW, flags=flags,
                    ignore_index=cfg.ignore_index, w_l1=cfg.w_l1, w_gd=cfg.w_gd, w_ssim=cfg.w_ssim,
