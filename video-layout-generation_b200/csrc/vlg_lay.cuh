@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
     const int64_t rho_end = min(rho + p.chunk, p.total_rows);
     float s_ce = 0.f, s_tvh = 0.f, s_tvw = 0.f;
     float m_disp = 0.f, m_grad = 0.f;
+    const float wreg = (p.class_weight && lane < K) ? __ldg(p.class_weight + lane) : 1.0f;   // class weights need K <= 32
     const float denom = GRAD ? (p.weighted_denom ? (float)__ldcg(&p.hdr->ce_denom) : (float)__ldcg(&p.hdr->n_valid)) : 1.0f;
     const float ce_unit = GRAD ? p.w_ce_over_scale / denom : 0.f;   // one division per thread, not one per pixel
     const T *src_all = reinterpret_cast<const T *>(p.src_layout);
@@ -331,8 +332,9 @@ __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_ker
             const bool lab_ok = lb >= 0 && lb < K;
             if (col_ok && !lab_ok && lb != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
             const int il = lab_ok ? (int)lb : 0;
-            float wl = 1.0f;
-            if (p.class_weight && lab_ok) wl = __ldg(p.class_weight + il);
+            // class weight of this pixel's label: lane k keeps weight k in a register (loaded once), so the loop has no
+            // dependent global load -- a predicated-off LDG here still cost a long-scoreboard round trip (14 % of stalls)
+            const float wl = __shfl_sync(FULL, wreg, il);
 
             float z[K], v[K];
             float vl[4];

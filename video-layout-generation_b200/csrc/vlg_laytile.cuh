@@ -40,10 +40,11 @@ template <int K>
 struct LayTileSmem {
     alignas(128) float win[2][kTSH * kTSW * K];
     alignas(128) float obuf[kTH][kTW * K];     // one output row of d(loss)/d(warped layout) per warp
-    float2 flow[2][kFH * kFW];
+    float2 flow[4][kFH * kFW];                  // tile i lives in flow[i & 3]: published two tiles ahead, no CTA barrier
     alignas(8) uint64_t bar[2];
     int acc[2][4];                              // sum of (x0 - x), sum of (y0 - y), pixels counted
     int org[2][2];                              // window origin (ox, oy)
+    unsigned cnt[2];                            // warps that have finished the tile using window buffer b
     float red[kTH][4];
     int last;
 };
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
     const T *src_all = reinterpret_cast<const T *>(p.src_layout);
 
     float s_ce = 0.f, s_tvh = 0.f, s_tvw = 0.f, m_disp = 0.f, m_grad = 0.f;
+    const float wreg = (p.class_weight && lane < K) ? __ldg(p.class_weight + lane) : 1.0f;   // class weights need K <= 32
 
     // geometry of a tile, advanced incrementally (row-major inside an image): no divisions in the loop
     struct TileGeo { int n, ty0, tx0; };
@@ -148,19 +150,21 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
     };
 
     // ---------------- prologue ----------------
-    if (tid < 2) mbar_init(&sm.bar[tid], 1);
+    if (tid < 2) { mbar_init(&sm.bar[tid], 1); sm.cnt[tid] = 0u; }
     if (tid < 8) sm.acc[tid >> 2][tid & 3] = 0;
-    float2 f0 = load_coords(0, g0), f1 = load_coords(1, g1), h1 = load_halo(1, g1);
+    float2 f0 = load_coords(0, g0), f1 = load_coords(1, g1);
     float2 xy0, xy1;
     {
-        const float2 h0 = load_halo(0, g0);
+        const float2 h0 = load_halo(0, g0), h1 = load_halo(1, g1);
         __syncthreads();
         xy0 = sample_and_accumulate(0, g0, f0, 0);
         xy1 = sample_and_accumulate(1, g1, f1, 1);
         publish_flow(0, f0, h0, 0);
+        publish_flow(1, f1, h1, 1);
     }
     __syncthreads();
     if (tid == 0 && nt > 0) issue_window(g0, 0);
+    if (tid == 0 && nt > 1) issue_window(g1, 1);
     __syncthreads();
     float2 pend_f = load_coords(2, g2), pend_h = load_halo(2, g2);
     int64_t pend_lab = load_label(0, g0);
@@ -176,16 +180,13 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
     for (int i = 0; i < nt; ++i) {
         const int b = i & 1;
         // ---- take over last iteration's loads, issue this iteration's ----
-        const float2 f2 = pend_f, h2 = pend_h;
+        const float2 f2 = pend_f, h2 = pend_h;   // coordinates / flow halo of tile i+2
         const int64_t lb = pend_lab;
         const float2 dc = pend_dc;
         pend_dc = load_dc(i + 1, g1);
         pend_f = load_coords(i + 3, g3);
         pend_h = load_halo(i + 3, g3);
         pend_lab = load_label(i + 1, g1);
-        // ---- window of tile i+1 ----
-        if (tid == 0 && i + 1 < nt) issue_window(g1, b ^ 1);
-
         // ---- tile i ----
         const TileGeo g = g0;
         const int y = g.ty0 + wid, x = g.tx0 + lane;
@@ -228,8 +229,9 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         const bool lab_ok = lb >= 0 && lb < K;
         if (inside && !lab_ok && lb != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
         const int il = lab_ok ? (int)lb : 0;
-        float wl = 1.0f;
-        if (p.class_weight && lab_ok) wl = __ldg(p.class_weight + il);
+        // class weight of this pixel's label: lane k keeps weight k in a register (loaded once), so the loop has no
+        // dependent global load -- a predicated-off LDG here still cost a long-scoreboard round trip (14 % of stalls)
+        const float wl = __shfl_sync(FULL, wreg, il);
 
         mbar_wait(&sm.bar[b], (unsigned)((i >> 1) & 1));     // window of tile i has landed
 
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         // ---- coordinate gradient: layout part + TV ----
         float gx = fmaf(tp.mx, gix, dc.x), gy = fmaf(tp.my, giy, dc.y);
         if (p.do_tv) {
-            const float2 *fc = &sm.flow[b][(wid + 1) * kFW + lane + 1];
+            const float2 *fc = &sm.flow[i & 3][(wid + 1) * kFW + lane + 1];
             const float2 f = f0, fdn = fc[kFW], fup = fc[-kFW], frt = fc[1], flt = fc[-1];
             const float cD = (inside && y + 1 < H) ? p.c_tvh : 0.f, cU = (inside && y >= 1) ? p.c_tvh : 0.f;
             const float cR = (inside && x + 1 < W) ? p.c_tvw : 0.f, cL = (inside && x >= 1) ? p.c_tvw : 0.f;
@@ -372,11 +374,23 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         }
         if (GRAD && p.d_coords && inside) reinterpret_cast<float2 *>(p.d_coords)[img + (int64_t)y * W + x] = make_float2(gx, gy);
 
-        // ---- prepare tiles i+2 (sampling positions, window origin) and i+1 (flow block) ----
+        // ---- prepare tile i+2: sampling positions, window origin sums, flow block ----
         const float2 xy2 = sample_and_accumulate(i + 2, g2, f2, b);
-        publish_flow(i + 1, f1, h1, b ^ 1);
-        __syncthreads();
-        f0 = f1; f1 = f2; h1 = h2;
+        publish_flow(i + 2, f2, h2, (i + 2) & 3);
+        // No CTA barrier: the LAST warp to finish tile i (which used window buffer b) issues the window of
+        // tile i+2 into that buffer.  Everything the other warps wrote for tile i+2 (origin sums, flow block)
+        // is ordered before that TMA by their fence + the counter, and every reader of tile i+2 waits for
+        // the TMA -- so warps may drift up to one tile apart instead of meeting at a barrier every tile.
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&sm.cnt[b], 1u) == (unsigned)(kTH - 1)) {
+                sm.cnt[b] = 0u;
+                __threadfence_block();
+                if (i + 2 < nt) issue_window(g2, b);
+            }
+        }
+        f0 = f1; f1 = f2;
         xy0 = xy1; xy1 = xy2;
         g0 = g1; g1 = g2; g2 = g3; g3 = advance(g3);
     }
