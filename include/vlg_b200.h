@@ -144,6 +144,14 @@ int vlg_warp_fwd_labels(const vlg_problem_t *prob, const void *src_rgb, const in
 int vlg_colorize(const vlg_problem_t *prob, const void *layout, const int64_t *label,
                  const uint8_t *lut_rgb, void *out_rgb, int64_t *out_label, void *stream);
 
+/* One-hot layout encoding (src/models/net_utils.py:14-24 transform_seg_one_hot:
+ * torch.eye(K)[seg.long()].permute(0,3,1,2)): label [N,H,W] as int64 XOR float32 class ids (the dataset
+ * hands float maps, src/folder.py:97-99; values are truncated like .long()) -> layout [N,H,W,K] of the
+ * problem's dtype.  Labels outside [0,K) raise VLG_STATUS_BAD_LABEL in `workspace`'s status word when a
+ * workspace is given and produce an all-zero pixel. */
+int vlg_one_hot(const vlg_problem_t *prob, const int64_t *label_i64, const float *label_f32,
+                void *out_layout, void *workspace, void *stream);
+
 /* Pass 1 of the fused op: warp + all loss terms + d(loss)/d(warped) + d(loss)/d(coords) in one
  * kernel.  Gradients are for an upstream grad of 1.0 (see vlg_scale_grads).
  *   tgt_rgb [N,H,W,3], tgt_label [N,H,W] i64

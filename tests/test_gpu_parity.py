@@ -516,3 +516,22 @@ def test_kernel_organisations_agree():
             for name, x, y in (("d_src_rgb", ga0, ga1), ("d_src_layout", gb0, gb1), ("d_flow", gf0, gf1)):
                 err = (x - y).abs().max().item()
                 assert err <= 1e-5 * y.abs().max().item(), (kw, name, err)   # the parity bar; typical 3e-6
+
+
+def test_one_hot_layout_matches_reference_encoding():
+    """`transform_seg_one_hot` (src/models/net_utils.py:14-24) on the device: int64 and float32 class-id
+    maps (the dataset hands float maps, src/folder.py:97-99), fp32 and bf16 layouts, K in {20, 19, 5}."""
+    g = torch.Generator().manual_seed(3)
+    for K in (20, 19, 5):
+        lab = torch.randint(0, K, (2, 37, 53), generator=g)
+        want = TO.one_hot_layout(lab, K)
+        for dt in (torch.float32, torch.bfloat16):
+            for src in (lab, lab.float(), lab.float()[:, None]):
+                got = vlg_b200.one_hot_layout(src.to(DEV), K, dt)
+                assert got.shape == (2, K, 37, 53) and got.dtype == dt
+                assert got.is_contiguous(memory_format=torch.channels_last)
+                assert torch.equal(got.float().cpu(), want)
+    # the encoded layout is a valid source of the fused op
+    d = _make_case(1, 40, 64, 20, 1.0, seed=4, layout="onehot")
+    lay = vlg_b200.one_hot_layout(d["src_layout"].argmax(1).to(DEV), 20)
+    assert torch.equal(lay.cpu(), d["src_layout"])

@@ -21,7 +21,7 @@ NEAR_RADIUS = 3
 LOSS_L1, LOSS_GD, LOSS_SSIM, LOSS_CE, LOSS_TV, LOSS_TOTAL, LOSS_NVALID, LOSS_MAXDISP, LOSS_SLOTS = range(9)
 
 EXPORTS = [
-    "vlg_version", "vlg_last_error", "vlg_workspace_bytes", "vlg_warp_fwd", "vlg_warp_fwd_labels", "vlg_colorize",
+    "vlg_version", "vlg_last_error", "vlg_workspace_bytes", "vlg_warp_fwd", "vlg_warp_fwd_labels", "vlg_colorize", "vlg_one_hot",
     "vlg_warp_loss_bwd_out",
     "vlg_warp_bwd_src", "vlg_reduce_partials", "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd",
     "vlg_scale_grads", "vlg_read_status", "vlg_launch_count",
@@ -80,6 +80,8 @@ def load(build_if_missing: bool = True):
     lib.vlg_warp_fwd_labels.argtypes = [P, vp, i64p, f32p, vp, i64p, vp]
     lib.vlg_colorize.argtypes = [P, vp, i64p, vp, vp, i64p, vp]
     lib.vlg_colorize.restype = C.c_int
+    lib.vlg_one_hot.argtypes = [P, i64p, f32p, vp, vp, vp]
+    lib.vlg_one_hot.restype = C.c_int
     lib.vlg_warp_loss_bwd_out.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, i64p, C.c_int, vp, C.c_size_t, vp]
     lib.vlg_warp_bwd_src.argtypes = [P, f32p, vp, vp, vp, C.c_size_t, vp]
     lib.vlg_reduce_partials.argtypes = [P, f32p, vp, C.c_size_t, vp]

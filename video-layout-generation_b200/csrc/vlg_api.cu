@@ -268,6 +268,40 @@ __global__ void __launch_bounds__(256) colorize_kernel(int64_t P, const T *__res
     store_px<T, 3>(out_rgb + i * 3, rgb);
 }
 
+// One-hot layout encoding (src/models/net_utils.py:14-24): one thread per 16-byte chunk of the output,
+// so a warp writes 512 contiguous bytes; the class id of a chunk's pixel is read once per chunk.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) one_hot_kernel(int64_t P, const int64_t *__restrict__ lab_i, const float *__restrict__ lab_f,
+                                                      T *__restrict__ out, WsHeader *hdr_or_null) {
+    constexpr int EPC = 16 / (int)sizeof(T);                    // elements per 16-byte chunk
+    constexpr bool kVec = (K % EPC) == 0;
+    constexpr int CPP = kVec ? K / EPC : 1;                     // chunks per pixel (1: scalar fallback, one thread per pixel)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * CPP) return;
+    const int64_t px = i / CPP;
+    const int chunk = (int)(i - px * CPP);
+    const int64_t l = lab_i ? __ldg(lab_i + px) : (int64_t)__ldg(lab_f + px);   // .long() truncation
+    if ((l < 0 || l >= K) && hdr_or_null && chunk == 0) atomicOr(&hdr_or_null->status, VLG_STATUS_BAD_LABEL);
+    if constexpr (kVec) {
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        T *e = reinterpret_cast<T *>(&r);
+        const int64_t rel = l - (int64_t)chunk * EPC;
+        if (rel >= 0 && rel < EPC) e[rel] = from_f<T>(1.0f);
+        reinterpret_cast<uint4 *>(out + px * K)[chunk] = r;
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[px * K + k] = from_f<T>(l == k ? 1.0f : 0.0f);
+    }
+}
+
+template <typename T, int K>
+static int launch_one_hot(int64_t P, const int64_t *lab_i, const float *lab_f, void *out, void *workspace, cudaStream_t st) {
+    constexpr int EPC = 16 / (int)sizeof(T);
+    const int64_t n = P * ((K % EPC) == 0 ? K / EPC : 1);
+    one_hot_kernel<T, K><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, lab_i, lab_f, (T *)out, (WsHeader *)workspace);
+    return check_launch("one_hot_kernel");
+}
+
 // forward-only warp (validation / rollout): one thread per output pixel
 template <typename T, int K>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, int64_t HW, const T *__restrict__ src_rgb,
@@ -683,6 +717,23 @@ int vlg_colorize(const vlg_problem_t *prob, const void *layout, const int64_t *l
     if (prob->K == k)                                                                                     \
         return prob->dtype == VLG_F32 ? launch_colorize<float, k>(P, layout, label, lut_rgb, out_rgb, out_label, st) \
                                       : launch_colorize<__nv_bfloat16, k>(P, layout, label, lut_rgb, out_rgb, out_label, st);
+    VLG_FOR_EACH_K(X)
+#undef X
+    return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
+}
+
+int vlg_one_hot(const vlg_problem_t *prob, const int64_t *label_i64, const float *label_f32, void *out_layout,
+                void *workspace, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if ((label_i64 == nullptr) == (label_f32 == nullptr)) return fail(VLG_ERR_ARG, "give exactly one of label_i64 / label_f32");
+    if (!out_layout) return fail(VLG_ERR_ARG, "out_layout is NULL");
+    const int64_t P = prob->N * prob->H * prob->W;
+    cudaStream_t st = (cudaStream_t)stream;
+#define X(k)                                                                                                  \
+    if (prob->K == k)                                                                                         \
+        return prob->dtype == VLG_F32 ? launch_one_hot<float, k>(P, label_i64, label_f32, out_layout, workspace, st) \
+                                      : launch_one_hot<__nv_bfloat16, k>(P, label_i64, label_f32, out_layout, workspace, st);
     VLG_FOR_EACH_K(X)
 #undef X
     return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");

@@ -213,6 +213,29 @@ def colorize(seg: torch.Tensor, n_classes: int = 20, argmax: bool = False, palet
 
 
 @torch.no_grad()
+def one_hot_layout(seg: torch.Tensor, n_classes: int = 20, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """`transform_seg_one_hot` (src/models/net_utils.py:14-24): class-id map -> one-hot layout.
+
+    `seg` is [N,H,W] or [N,1,H,W], int64 or float32 class ids (the dataset hands float maps,
+    src/folder.py:97-99; truncated like `.long()`).  Returns an NCHW-logical [N,K,H,W] tensor in NHWC
+    storage, ready to be a `src_layout` -- so a data pipeline uploads 4-8 bytes per pixel instead of 4*K."""
+    _require_cuda(seg)
+    if seg.dim() == 4:
+        if seg.shape[1] != 1:
+            raise VlgError("one_hot_layout expects class ids of shape [N,H,W] or [N,1,H,W]")
+        seg = seg[:, 0]
+    if seg.dtype not in (torch.int64, torch.float32):
+        raise VlgError("one_hot_layout expects int64 or float32 class ids")
+    seg = seg.contiguous()
+    N, H, W = seg.shape
+    prob = _problem(N, H, W, n_classes, dtype, WarpLossConfig())
+    out = empty_nhwc((N, n_classes, H, W), dtype, seg.device)
+    lib = _cabi.load()
+    li, lf = (_ptr(seg), None) if seg.dtype == torch.int64 else (None, _ptr(seg))
+    check(lib.vlg_one_hot(C.byref(prob), li, lf, _ptr(out), None, _stream()))
+    return out
+
+
 def rollout(img: torch.Tensor, label: torch.Tensor, flow_fn, steps: int = 5, *, padding_mode: str = "border"):
     """Autoregressive rollout (shape of src/trainer.py:453-476, which runs 8 steps and feeds the
     argmax back): step t warps the previous frame and label map with `flow_fn(t, img, label)`
