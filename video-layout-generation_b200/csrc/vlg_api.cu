@@ -375,6 +375,30 @@ static bool make_layout_map(const vlg_problem_t *prob, const void *src_layout, C
     return r == CUDA_SUCCESS;
 }
 
+// Tensor map of an NHWC layout for the persistent tile kernel.  Pixels whose byte size is a multiple of 16
+// use the 4-D element-typed map above; 8-byte-multiple pixels (20 bf16 channels = 40 B) are described as
+// rows of 8-byte units: 3-D {W*PXB/8, H, N}, box {box_w*PXB/8, box_h, 1}.  *px8 tells which one was built.
+static bool make_window_map(const vlg_problem_t *prob, const void *src_layout, CUtensorMap *map, int box_w, int box_h, bool *px8) {
+    *px8 = false;
+    if (prob->dtype == VLG_F32) return make_layout_map(prob, src_layout, map, box_w, box_h);
+    memset(map, 0, sizeof(*map));
+    const size_t pxb = (size_t)prob->K * 2;
+    if (pxb % 8 != 0 || ((size_t)prob->W * pxb) % 16 != 0 || ((uintptr_t)src_layout) % 16 != 0) return false;
+    const size_t upp = pxb / 8;   // 8-byte units per pixel
+    if ((size_t)box_w * upp > 256) return false;
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)prob->W * upp, (cuuint64_t)prob->H, (cuuint64_t)prob->N};
+    const cuuint64_t gstr[2] = {(cuuint64_t)prob->W * pxb, (cuuint64_t)prob->H * prob->W * pxb};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_w * upp), (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(src_layout), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    *px8 = r == CUDA_SUCCESS;
+    return r == CUDA_SUCCESS;
+}
+
 template <typename T, int K>
 static int launch_pass1(bool warp, const Pass1Params &pp, const CUtensorMap &lay_map, int64_t n_blocks, cudaStream_t st) {
     // the staged source window is the last member: the un-warped criteria do not allocate it
@@ -503,18 +527,18 @@ static int launch_lay(LayParams lp, const CUtensorMap &map, bool grad, cudaStrea
 }
 
 // Persistent launch of the double-buffered layout tile kernel: one wave of resident CTAs.
-template <int K>
+template <typename T, int K, bool PX8>
 static int launch_laytile(const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
-    const size_t smem = sizeof(LayTileSmem<K>);
+    const size_t smem = sizeof(LayTileSmem<T, K>);
     static int ctas_resident = 0;
     if (!ctas_resident) {
-        cudaError_t e = cudaFuncSetAttribute(lay_tile_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(lay_tile_kernel<T, K, true, PX8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(lay_tile_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(lay_tile_kernel<T, K, false, PX8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         if (e == cudaSuccess) e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lay_tile_kernel<K, true>, kThreads, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lay_tile_kernel<T, K, true, PX8>, kThreads, smem);
         if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "lay_tile_kernel setup: %s", cudaGetErrorString(e));
         ctas_resident = sms * per_sm;
     }
@@ -522,16 +546,23 @@ static int launch_laytile(const LayParams &lp, const CUtensorMap &map, bool grad
     int64_t blocks = ctas_resident < kLayMaxWarps ? ctas_resident : kLayMaxWarps;
     if (blocks * 2 > n_tiles) blocks = (n_tiles + 1) / 2;    // at least two tiles per CTA keeps the pipeline meaningful
     if (blocks < 1) blocks = 1;
-    if (grad) lay_tile_kernel<K, true><<<(unsigned)blocks, kThreads, smem, st>>>(lp, map);
-    else lay_tile_kernel<K, false><<<(unsigned)blocks, kThreads, smem, st>>>(lp, map);
+    if (grad) lay_tile_kernel<T, K, true, PX8><<<(unsigned)blocks, kThreads, smem, st>>>(lp, map);
+    else lay_tile_kernel<T, K, false, PX8><<<(unsigned)blocks, kThreads, smem, st>>>(lp, map);
     return check_launch("lay_tile_kernel");
 }
 
-static int dispatch_laytile(const vlg_problem_t *prob, const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
-#define X(k) if constexpr ((k) % 4 == 0) { if (prob->K == k) return launch_laytile<k>(lp, map, grad, st); }
+static int dispatch_laytile(const vlg_problem_t *prob, const LayParams &lp, const CUtensorMap &map, bool px8, bool grad, cudaStream_t st) {
+#define X(k)                                                                                                   \
+    if constexpr ((k) % 4 == 0) {                                                                              \
+        if (prob->K == k) {                                                                                    \
+            if (prob->dtype == VLG_F32) return launch_laytile<float, k, false>(lp, map, grad, st);             \
+            if (px8) return launch_laytile<__nv_bfloat16, k, true>(lp, map, grad, st);                         \
+            if constexpr ((k) % 8 == 0) return launch_laytile<__nv_bfloat16, k, false>(lp, map, grad, st);     \
+        }                                                                                                      \
+    }
     VLG_FOR_EACH_K(X)
 #undef X
-    return fail(VLG_ERR_UNSUPPORTED, "layout tile kernel: K not compiled in");
+    return fail(VLG_ERR_UNSUPPORTED, "layout tile kernel: K / dtype not compiled in");
 }
 
 static int dispatch_lay(const vlg_problem_t *prob, const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
@@ -616,10 +647,11 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     }
     int rc = VLG_OK;
     bool lay_done = false;
-    if (warp && has_lay && prob->dtype == VLG_F32 && prob->K % 4 == 0 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_TILE_LAYOUT))) {
+    if (warp && has_lay && prob->K % 4 == 0 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_TILE_LAYOUT))) {
         CUtensorMap row_map;
-        const bool strips = (prob->flags & VLG_FLAG_STRIP_LAYOUT) != 0;
-        if (strips ? make_layout_map(prob, src_layout, &row_map, kLBW, 1) : make_layout_map(prob, src_layout, &row_map, kTSW, kTSH)) {
+        bool px8 = false;
+        const bool strips = (prob->flags & VLG_FLAG_STRIP_LAYOUT) != 0 && prob->dtype == VLG_F32;
+        if (strips ? make_layout_map(prob, src_layout, &row_map, kLBW, 1) : make_window_map(prob, src_layout, &row_map, kTSW, kTSH, &px8)) {
             LayParams lp{};
             lp.cc = pp.cc;
             lp.N = pp.N; lp.strips = pp.tiles_x; lp.tiles_y = pp.tiles_y;
@@ -635,7 +667,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.partials = (float *)(ws + L.partials_lay);
             lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
             lp.red = pp.red; lp.hdr = hdr;
-            rc = strips ? dispatch_lay(prob, lp, row_map, need_grad, st) : dispatch_laytile(prob, lp, row_map, need_grad, st);
+            rc = strips ? dispatch_lay(prob, lp, row_map, need_grad, st) : dispatch_laytile(prob, lp, row_map, px8, need_grad, st);
             if (rc) return rc;
             lay_done = true;
         }

@@ -30,15 +30,25 @@
 
 namespace vlg {
 
+// four consecutive channels from shared memory as fp32 (one 128-bit / 64-bit load)
+template <typename T> __device__ __forceinline__ float4 load4_smem(const T *p);
+template <> __device__ __forceinline__ float4 load4_smem<float>(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+template <> __device__ __forceinline__ float4 load4_smem<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162 *>(&r.x), hi = *reinterpret_cast<const __nv_bfloat162 *>(&r.y);
+    const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 constexpr int kTSW = 40, kTSH = 12;   // staged window (pixels)
 constexpr int kFW = kTW + 2, kFH = kTH + 2;   // flow block with a halo of one pixel (TV stencil)
 #ifndef VLG_LAYTILE_MIN_BLOCKS
 #define VLG_LAYTILE_MIN_BLOCKS 2
 #endif
 
-template <int K>
+template <typename T, int K>
 struct LayTileSmem {
-    alignas(128) float win[2][kTSH * kTSW * K];
+    alignas(128) T win[2][kTSH * kTSW * K];
     alignas(128) float obuf[kTH][kTW * K];     // one output row of d(loss)/d(warped layout) per warp
     float2 flow[4][kFH * kFW];                  // tile i lives in flow[i & 3]: published two tiles ahead, no CTA barrier
     alignas(8) uint64_t bar[2];
@@ -49,18 +59,20 @@ struct LayTileSmem {
     int last;
 };
 
-template <int K, bool GRAD>
+// PX8: the tensor map describes rows of 8-byte units (pixels whose byte size is not a multiple of 16, e.g.
+// 20 bf16 channels = 40 B): 3-D map {W*PXB/8, H, N}, window origin scaled by PXB/8.
+template <typename T, int K, bool GRAD, bool PX8>
 __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_kernel(const LayParams p,
                                                                                    const __grid_constant__ CUtensorMap win_map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using T = float;
-    LayTileSmem<K> &sm = *reinterpret_cast<LayTileSmem<K> *>(smem_raw);
+    LayTileSmem<T, K> &sm = *reinterpret_cast<LayTileSmem<T, K> *>(smem_raw);
     const CoordCfg &cc = p.cc;
     const int H = cc.H, W = cc.W;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31;
     const int wid = __shfl_sync(FULL, tid >> 5, 0);
-    constexpr unsigned kWinBytes = (unsigned)(kTSH * kTSW * K * sizeof(float));
+    constexpr unsigned kWinBytes = (unsigned)(kTSH * kTSW * K * sizeof(T));
+    constexpr int PXB = K * (int)sizeof(T);
     const int tiles_x = p.strips, tiles_y = p.tiles_y;
     const int tiles_img = tiles_x * tiles_y;
 
@@ -145,11 +157,14 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         const int sx_ = sm.acc[buf][0], sy_ = sm.acc[buf][1];
         // floor division of the sums (C division truncates towards zero)
         const int mdx = (sx_ >= 0 ? sx_ : sx_ - cnt + 1) / cnt, mdy = (sy_ >= 0 ? sy_ : sy_ - cnt + 1) / cnt;
-        const int ox = g.tx0 + mdx - (kTSW - kTW - 2) / 2, oy = g.ty0 + mdy - (kTSH - kTH - 2) / 2;
+        int ox = g.tx0 + mdx - (kTSW - kTW - 2) / 2;
+        const int oy = g.ty0 + mdy - (kTSH - kTH - 2) / 2;
+        if (PX8 && (PXB % 16) != 0) ox &= ~1;   // TMA needs a 16-byte aligned start: 40-byte pixels -> even column
         sm.org[buf][0] = ox; sm.org[buf][1] = oy;
         sm.acc[buf][0] = 0; sm.acc[buf][1] = 0; sm.acc[buf][2] = 0;
         mbar_expect_tx(&sm.bar[buf], kWinBytes);
-        tma_load_4d(sm.win[buf], &win_map, &sm.bar[buf], 0, ox, oy, g.n);
+        if (PX8) tma_load_3d(sm.win[buf], &win_map, &sm.bar[buf], ox * (PXB / 8), oy, g.n);
+        else tma_load_4d(sm.win[buf], &win_map, &sm.bar[buf], 0, ox, oy, g.n);
     };
 
     // ---------------- prologue ----------------
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         }
         if (st0) {
             const T *st1 = st0 + kTSW * K;
-            vl[0] = st0[il]; vl[1] = st0[K + il]; vl[2] = st1[il]; vl[3] = st1[K + il];
+            vl[0] = to_f<T>(st0[il]); vl[1] = to_f<T>(st0[K + il]); vl[2] = to_f<T>(st1[il]); vl[3] = to_f<T>(st1[K + il]);
             const float2 nw2 = make_float2(tp.nw, tp.nw), ne2 = make_float2(tp.ne, tp.ne);
             const float2 sw2 = make_float2(tp.sw, tp.sw), se2 = make_float2(tp.se, tp.se);
             float m_run = -3.0e38f;
@@ -265,8 +280,8 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
             se = 0.f;
 #pragma unroll
             for (int c = 0; c < K / 4; ++c) {
-                const float4 a = *reinterpret_cast<const float4 *>(st0 + 4 * c), bq = *reinterpret_cast<const float4 *>(st0 + K + 4 * c);
-                const float4 cq = *reinterpret_cast<const float4 *>(st1 + 4 * c), dq = *reinterpret_cast<const float4 *>(st1 + K + 4 * c);
+                const float4 a = load4_smem<T>(st0 + 4 * c), bq = load4_smem<T>(st0 + K + 4 * c);
+                const float4 cq = load4_smem<T>(st1 + 4 * c), dq = load4_smem<T>(st1 + K + 4 * c);
                 // bit-exact FMA chain of Appendix A.6 on channel pairs
                 float2 z01 = __fmul2_rn(make_float2(a.x, a.y), nw2), z23 = __fmul2_rn(make_float2(a.z, a.w), nw2);
                 z01 = __ffma2_rn(make_float2(bq.x, bq.y), ne2, z01); z23 = __ffma2_rn(make_float2(bq.z, bq.w), ne2, z23);

@@ -140,6 +140,14 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // sampling coordinates from raw coords + the smem base-grid table
 __device__ __forceinline__ float2 source_xy(const CoordCfg &cc, float2 c, float bx, float by, float &mx, float &my) {
     float gx = c.x, gy = c.y;
