@@ -54,6 +54,8 @@ extern "C" {
 #define VLG_FLAG_TILE_LAYOUT 8u /* evaluate the layout terms in the first (non-persistent) tile kernel            */
 #define VLG_FLAG_STRIP_LAYOUT 16u /* evaluate the layout terms in the per-warp row-ring strip kernel instead of the
                                    * persistent double-buffered tile kernel                                          */
+#define VLG_FLAG_PASS2_COORDS 32u /* pass 2 re-derives the tap cells and weights from the coordinates (pass2_kernel)
+                                   * instead of reading the tap records pass 1 wrote (pass2_rec_kernel)              */
 
 /* term_mask bits */
 #define VLG_TERM_L1 1u

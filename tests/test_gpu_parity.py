@@ -518,6 +518,34 @@ def test_kernel_organisations_agree():
                 assert err <= 1e-5 * y.abs().max().item(), (kw, name, err)   # the parity bar; typical 3e-6
 
 
+def test_pass2_from_records_matches_pass2_from_coords_bitwise():
+    """Pass 2 exists twice: pass2_rec_kernel gathers from the tap records pass 1 wrote (TMA-staged windows of
+    d_out, cell codes and fractional weights), pass2_kernel re-derives them from the coordinates.  Same
+    candidate order, same weights: d_src_rgb / d_src_layout must be bit-identical -- for odd widths (pitched
+    rows), both paddings, far pixels (fixed-point path), bf16 and every pass-1 organisation (lay_tile_kernel
+    writes the records itself, the others go through tap_records_kernel)."""
+    cases = ((0.6, "border", (2, 77, 141), {}), (5.0, "zeros", (2, 77, 141), {}), (2.0, "border", (1, 19, 33), {}),
+             (30.0, "border", (2, 64, 200), {}), (2.5, "zeros", (1, 40, 250), dict(layout_kernel="strip")),
+             (2.5, "border", (1, 40, 250), dict(tile_kernels=True)), (1.5, "border", (2, 375 // 5, 1242 // 6), {}))
+    for sigma, padding, shape, kw in cases:
+        d = _make_case(*shape, 20, sigma, seed=23, layout="soft")
+        for dt in (torch.float32, torch.bfloat16):
+            if dt == torch.bfloat16 and kw:
+                continue
+            res = []
+            for rec in (True, False):
+                a = _cl(d["src_rgb"].to(dt)).requires_grad_(True)
+                b = _cl(d["src_layout"].to(dt)).requires_grad_(True)
+                f = d["flow"].to(DEV).requires_grad_(True)
+                cfg = vlg_b200.WarpLossConfig(w_tv=0.4, padding_mode=padding, pass2_records=rec, **kw)
+                total, vec, _ = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"].to(dt)), d["tgt_label"].to(DEV), cfg)
+                total.backward()
+                res.append((vec.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+            for x, y in zip(*res):
+                assert torch.equal(x, y), (sigma, padding, shape, kw, dt)
+            assert res[0][2].abs().max().item() > 0
+
+
 def test_one_hot_layout_matches_reference_encoding():
     """`transform_seg_one_hot` (src/models/net_utils.py:14-24) on the device: int64 and float32 class-id
     maps (the dataset hands float maps, src/folder.py:97-99), fp32 and bf16 layouts, K in {20, 19, 5}."""

@@ -79,10 +79,14 @@ static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
     L.partials_rgb = off; off = align_up(off + (size_t)kRgbMaxWarps * kRgbSlots * sizeof(float), 256);
     L.partials_lay = off; off = align_up(off + (size_t)kLayMaxWarps * 4 * sizeof(float), 256);
     L.flagged = off; off = align_up(off + (size_t)L.n_blocks * sizeof(int), 256);
-    L.dout_rgb = L.dout_lay = L.far_acc = L.far_list = 0;
+    L.dout_rgb = L.dout_lay = L.far_acc = L.far_list = L.rec_code = L.rec_frac = 0;
+    L.pitch = (int64_t)align_up((size_t)p->W, 4);
     if (with_src_grad) {
-        L.dout_rgb = off; off = align_up(off + P * 3 * sizeof(float), 256);
+        const size_t Pp = (size_t)p->N * p->H * (size_t)L.pitch;   // pitched rows: TMA-describable (16-byte row starts)
+        L.dout_rgb = off; off = align_up(off + Pp * 3 * sizeof(float), 256);
         L.dout_lay = off; off = align_up(off + P * p->K * sizeof(float), 256);
+        L.rec_code = off; off = align_up(off + Pp * sizeof(uint32_t), 256);
+        L.rec_frac = off; off = align_up(off + Pp * sizeof(float2), 256);
         if (!(p->flags & VLG_FLAG_NO_FAR_PATH)) {
             L.far_acc = off; off = align_up(off + P * (3 + p->K) * sizeof(long long), 256);
             L.far_list = off; off = align_up(off + P * sizeof(int), 256);
@@ -399,6 +403,28 @@ static bool make_window_map(const vlg_problem_t *prob, const void *src_layout, C
     return r == CUDA_SUCCESS;
 }
 
+// Pass 2 gathers from the tap records pass 1 wrote (pass2_rec_kernel: all staging by TMA) when the d_out
+// windows can be described by tensor maps; otherwise, or on request, it re-derives the records from the
+// coordinates (pass2_kernel).  Both calls of a step evaluate this with the same problem descriptor.
+static bool pass2_from_records(const vlg_problem_t *prob) {
+    return prob->K % 4 == 0 && prob->K <= 64 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_PASS2_COORDS)) && tensor_map_encoder() != nullptr;
+}
+
+// Tensor map of a pitched workspace array [N][H][pitch * epp] of 4-byte elements (epp elements per pixel) with a
+// window of kQW2 x kQH pixels.
+static bool make_pitched_map(const vlg_problem_t *prob, const void *base, int64_t pitch, int epp, CUtensorMapDataType dt, CUtensorMap *map) {
+    memset(map, 0, sizeof(*map));
+    if (((uintptr_t)base) % 16 != 0 || (pitch * epp * 4) % 16 != 0) return false;
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)(pitch * epp), (cuuint64_t)prob->H, (cuuint64_t)prob->N};
+    const cuuint64_t gstr[2] = {(cuuint64_t)(pitch * epp * 4), (cuuint64_t)(prob->H * pitch * epp * 4)};
+    const cuuint32_t box[3] = {(cuuint32_t)(kQW2 * epp), (cuuint32_t)kQH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, dt, 3, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T, int K>
 static int launch_pass1(bool warp, const Pass1Params &pp, const CUtensorMap &lay_map, int64_t n_blocks, cudaStream_t st) {
     // the staged source window is the last member: the un-warped criteria do not allocate it
@@ -441,6 +467,25 @@ static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_p
         far_scatter_kernel<K><<<148 * 2, 256, 0, st>>>(pp);
         rc = check_launch("far_scatter_kernel");
         if (rc) return rc;
+    }
+    if constexpr (K % 4 == 0 && K <= 64) {
+        CUtensorMap lay_map, rgb_map, frac_map, code_map;
+        if (pass2_from_records(prob) && pp.rec_code && pp.rec_frac &&
+            make_layout_map(prob, pp.d_out_lay, &lay_map, kQW, kQH, true) &&
+            make_pitched_map(prob, pp.d_out_rgb, pp.pitch, 3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, &rgb_map) &&
+            make_pitched_map(prob, pp.rec_frac, pp.pitch, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, &frac_map) &&
+            make_pitched_map(prob, pp.rec_code, pp.pitch, 1, CU_TENSOR_MAP_DATA_TYPE_UINT32, &code_map)) {
+            constexpr size_t smem_rec = sizeof(Pass2RecSmem<K>);
+            static bool rec_attr_done = false;  // per instantiation
+            if (!rec_attr_done) {
+                cudaError_t e = cudaFuncSetAttribute(pass2_rec_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
+                if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass2_rec): %s", cudaGetErrorString(e));
+                rec_attr_done = true;
+            }
+            pass2_rec_kernel<T, K><<<dim3((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N), kThreads, smem_rec, st>>>(
+                pp, lay_map, rgb_map, frac_map, code_map);
+            return check_launch("pass2_rec_kernel");
+        }
     }
     constexpr size_t smem = pass2_smem_bytes<K>();
     static bool attr_done = false;  // per instantiation
@@ -622,6 +667,10 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
     pp.hdr = hdr;
     pp.flags = prob->flags;
+    pp.pitch = (int)L.pitch;
+    // tap records for pass 2: written by lay_tile_kernel on its way, by tap_records_kernel after the other organisations
+    const bool want_records = warp && need_grad && d_out_lay != nullptr && L.rec_code != 0 && pass2_from_records(prob);
+    bool records_done = false;
     // The rgb terms run in the column-strip kernel, launched BEFORE the kernel that owns the layout / TV
     // terms: it stores its part of d(loss)/d(coords) (and the label count); the layout kernel, which has
     // issue slots to spare, loads that part one tile ahead, adds its own and performs the final reduction.
@@ -638,6 +687,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
         rp.c_ssim = (pp.terms & VLG_TERM_SSIM) ? pp.c_ssim : 0.f;
         rp.d_coords = need_grad ? d_coords : nullptr;
         rp.d_out_rgb = need_grad ? (float *)d_out_rgb : nullptr;
+        rp.pitch = (int)L.pitch;
         rp.partials = (float *)(ws + L.partials_rgb);
         rp.hdr = hdr;
         int rc0 = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
@@ -663,6 +713,10 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.accum_dcoords = pp.accum_dcoords;
             lp.d_coords = need_grad ? d_coords : nullptr;
             lp.d_out_lay = need_grad ? (float *)d_out_lay : nullptr;
+            if (want_records && !strips) {
+                lp.rec_code = (uint32_t *)(ws + L.rec_code); lp.rec_frac = (float2 *)(ws + L.rec_frac); lp.pitch = (int)L.pitch;
+                records_done = true;
+            }
             lp.out_argmax = out_argmax;
             lp.partials = (float *)(ws + L.partials_lay);
             lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
@@ -678,6 +732,11 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
         if (!pp.use_tma) memset(&lay_map, 0, sizeof(lay_map));
         rc = dispatch_pass1(prob, warp, pp, lay_map, L.n_blocks, st);
         if (rc) return rc;
+    }
+    if (want_records && !records_done) {
+        tap_records_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pp.cc, P, prob->H * prob->W, (int)L.pitch, (const float2 *)coords,
+                                                                        (uint32_t *)(ws + L.rec_code), (float2 *)(ws + L.rec_frac));
+        rc = check_launch("tap_records_kernel");
     }
     return rc;
 }
@@ -808,6 +867,9 @@ int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src
     pp.coords = coords;
     pp.d_out_rgb = (const float *)(ws + L.dout_rgb);
     pp.d_out_lay = (const float *)(ws + L.dout_lay);
+    pp.rec_code = (const uint32_t *)(ws + L.rec_code);
+    pp.rec_frac = (const float2 *)(ws + L.rec_frac);
+    pp.pitch = (int)L.pitch;
     pp.d_src_rgb = d_src_rgb; pp.d_src_lay = d_src_layout;
     pp.far_acc = L.far_acc ? (long long *)(ws + L.far_acc) : nullptr;
     pp.far_list = L.far_list ? (const int *)(ws + L.far_list) : nullptr;

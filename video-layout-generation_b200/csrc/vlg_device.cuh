@@ -113,7 +113,10 @@ __host__ __device__ __forceinline__ int64_t dout_index(int64_t n, int64_t HW, in
 
 struct WsLayout {
     size_t header, tile_flags, tile_disp, partials, partials_rgb, partials_lay, flagged, dout_rgb, dout_lay, far_acc, far_list, total;
+    size_t rec_code, rec_frac;   // tap records of pass 1 for pass 2 (pitched rows)
     int64_t n_blocks;
+    int64_t pitch;               // row pitch (pixels) of dout_rgb / rec_code / rec_frac: W rounded up to 4, so that every
+                                 // row starts on a 16-byte boundary and the arrays can be described by TMA tensor maps
 };
 
 // ---------------------------------------------------------------- tiling of pass 1
@@ -277,6 +280,17 @@ __device__ __forceinline__ Taps make_taps(const CoordCfg &cc, float2 c, int y, i
 __device__ __forceinline__ float tap_displacement(const CoordCfg &cc, const Taps &t, int y, int x) {
     if (t.x0 < -1 || t.x0 >= cc.W || t.y0 < -1 || t.y0 >= cc.H) return 0.0f;
     return fmaxf(fabsf(t.ix - (float)x), fabsf(t.iy - (float)y));
+}
+
+// Tap record of one output pixel, written by pass 1 and consumed by pass 2 (the transpose of the gather):
+// the cell of the NW tap relative to the pixel itself, packed as (x0 - x + 8) | (y0 - y + 8) << 16, or 0
+// when the pixel contributes nothing through the near path (all taps outside the image, or displaced by
+// >= VLG_NEAR_RADIUS: those travel through the fixed-point far path).  A valid code is never 0 -- which
+// is also what the TMA zero-fill hands pass 2 for cells outside the image.
+__device__ __forceinline__ uint32_t tap_cell_code(const CoordCfg &cc, const Taps &t, int y, int x) {
+    const bool dead = t.x0 < -1 || t.x0 >= cc.W || t.y0 < -1 || t.y0 >= cc.H;
+    const bool far = fmaxf(fabsf(t.ix - (float)x), fabsf(t.iy - (float)y)) >= (float)VLG_NEAR_RADIUS;
+    return (dead || far) ? 0u : ((uint32_t)(t.x0 - x + 8) | ((uint32_t)(t.y0 - y + 8) << 16));
 }
 
 // Bilinear gather of C channels at one output pixel from an NHWC image plane `img` (batch n

@@ -76,6 +76,9 @@ struct LayParams {
     int accum_dcoords;             // d_coords already holds the rgb part (the rgb strip kernel ran before): add to it
     float *d_coords;               // nullable (validation)
     float *d_out_lay;              // [P][K] fp32 staging, nullable
+    uint32_t *rec_code;            // [N][H][pitch] tap records for pass 2 (tap_cell_code), nullable: lay_tile_kernel only
+    float2 *rec_frac;              // [N][H][pitch] fractional tap weights (ix - x0, iy - y0)
+    int pitch;
     int64_t *out_argmax;           // nullable
     float *partials;               // [n_warps][4]: ce, tv_h, tv_w, -
     float *tile_disp;              // [n_tiles] max NEAR displacement per 32x8 tile (zero-initialised, atomicMax)

@@ -244,6 +244,12 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
             }
         }
 
+        if (GRAD && p.rec_code && inside) {   // tap record for pass 2: which source cell this pixel feeds, with which weights
+            const int64_t ro = ((int64_t)g.n * H + y) * p.pitch + x;
+            p.rec_code[ro] = tap_cell_code(cc, tp, y, x);
+            p.rec_frac[ro] = make_float2(tp.ix - tp.fx0, tp.iy - tp.fy0);
+        }
+
         const bool lab_ok = lb >= 0 && lb < K;
         if (inside && !lab_ok && lb != p.ignore_index) atomicOr(&p.hdr->status, VLG_STATUS_BAD_LABEL);
         const int il = lab_ok ? (int)lb : 0;

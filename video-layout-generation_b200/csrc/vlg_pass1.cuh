@@ -47,8 +47,9 @@ struct Pass1Params {
     uint32_t terms;         // VLG_TERM_* bits to evaluate
     // outputs
     float *d_coords;        // WARP && need_grad
-    void *d_out_rgb;        // WARP: fp32 staging (nullable). !WARP: user tensor of type T (nullable)
+    void *d_out_rgb;        // WARP: fp32 staging, rows of `pitch` pixels (nullable). !WARP: user tensor of type T (nullable)
     void *d_out_lay;
+    int pitch;              // row pitch (pixels) of the WARP d_out_rgb staging
     int64_t *out_argmax;    // nullable
     float *partials;        // [n_blocks][kPartialSlots]
     float *tile_disp;       // [n_blocks] max displacement among the tile's NEAR output pixels (WARP)
@@ -602,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                         gix += (dt4[1] - dt4[0]) * wy0 + (dt4[3] - dt4[2]) * wy1;
                         giy += (dt4[2] - dt4[0]) * wx0 + (dt4[3] - dt4[1]) * wx1;
                     }
-                    if (p.d_out_rgb) store_px<float, 3>(reinterpret_cast<float *>(p.d_out_rgb) + (img_px + o) * 3, dr);
+                    if (p.d_out_rgb) store_px<float, 3>(reinterpret_cast<float *>(p.d_out_rgb) + (((int64_t)n * H + y) * p.pitch + x) * 3, dr);
                 } else if (p.d_out_rgb) {
                     store_px<T, 3>(reinterpret_cast<T *>(p.d_out_rgb) + (img_px + o) * 3, dr);
                 }

@@ -23,8 +23,11 @@ struct Pass2Params {
     CoordCfg cc;
     int N, tiles_x, tiles_y;
     const float *coords;
-    const float *d_out_rgb;   // fp32 staging written by pass 1
-    const float *d_out_lay;
+    const float *d_out_rgb;   // fp32 staging written by pass 1: [N][H][pitch][3]
+    const float *d_out_lay;   // [N][H][W][K]
+    const uint32_t *rec_code; // [N][H][pitch] tap records written by pass 1 (tap_cell_code)
+    const float2 *rec_frac;   // [N][H][pitch]
+    int pitch;                // row pitch (pixels) of d_out_rgb / rec_code / rec_frac
     void *d_src_rgb;          // type T, nullable
     void *d_src_lay;
     long long *far_acc;       // [P][3+K] fixed point, nullable (VLG_FLAG_NO_FAR_PATH)
@@ -122,8 +125,10 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_kernel(const Pass2Params p,
                 for (int i = lane; i < (xb - xa) * K; i += 32) s_lay[(size_t)c0 * K + i] = __ldg(p.d_out_lay + g0 * K + i);
             }
         }
-        if (want_rgb)   // 12-byte pixels: 4-byte cp.async (no register round trip, completes with the group)
-            for (int i = lane; i < (xb - xa) * 3; i += 32) cp_async4(s_rgb + q0 * 3 + i, p.d_out_rgb + g0 * 3 + i);
+        if (want_rgb) {   // 12-byte pixels: 4-byte cp.async (no register round trip, completes with the group)
+            const float *rsrc = p.d_out_rgb + (((int64_t)n * H + y) * p.pitch + xa) * 3;
+            for (int i = lane; i < (xb - xa) * 3; i += 32) cp_async4(s_rgb + q0 * 3 + i, rsrc + i);
+        }
     }
     // ---- sampling coordinates of the candidate output pixels ----
     // flat index over the region, addresses clamped into the image: the (up to three) coords loads of
@@ -244,6 +249,154 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_kernel(const Pass2Params p,
     }
 }
 
+
+// ---- pass 2 from tap records: everything the gather needs arrives by TMA ----
+// pass2_kernel above re-derives, per CTA, the tap cell and weights of all 532 candidate output pixels
+// from the coordinates (source_xy -> floor -> code) and copies the rgb part of d_out row by row: 28 %
+// of its instructions and two of its three barriers.  Here pass 1 has already written a 12-byte record
+// per output pixel (cell code + the two fractional weights, tap_cell_code), rows padded to a pitch of
+// 4 pixels, so the CTA's whole input is four TMA tensor loads on one mbarrier:
+//   d_out_lay window  [kQH][kQW][K]      (as before)
+//   d_out_rgb window  [kQH][kQW2 * 3]    fp32
+//   fraction window   [kQH][kQW2]        float2
+//   code window       [kQH][kQW2]        uint32 -- out-of-image cells arrive as 0 = "no contribution"
+// the first anchored at (tx0 - kRMax, ty0 - kRMax), the narrow-pixel ones at (tx0 - kQX2, ty0 - kRMax): a TMA box must
+// start on a 16-byte boundary, i.e. on a column that is a multiple of 4 for the 12-, 8- and 4-byte pixels.  The scan / hit loop is the same as pass2_kernel's, in the
+// same order, so both kernels produce bit-identical gradients.
+constexpr int kQW2 = 40;   // window width of the 12-, 8- and 4-byte-pixel arrays: rows of 480 / 320 / 160 bytes
+constexpr int kQX2 = 4;    // their left margin (>= kRMax, multiple of 4; kTW is a multiple of 4 too)
+static_assert(kQX2 >= kRMax && kQX2 % 4 == 0 && kTW % 4 == 0 && kQX2 + kTW + kRMax <= kQW2, "narrow-pixel window geometry");
+
+template <int K>
+struct Pass2RecSmem {
+    alignas(128) float lay[kQN * K];
+    alignas(128) float rgb[kQH * kQW2 * 3];
+    alignas(128) float2 frac[kQH * kQW2];
+    alignas(128) uint32_t code[kQH * kQW2];
+    alignas(8) uint64_t bar;
+};
+
+template <typename T, int K>
+__global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Params p, const __grid_constant__ CUtensorMap lay_map,
+                                                                const __grid_constant__ CUtensorMap rgb_map,
+                                                                const __grid_constant__ CUtensorMap frac_map,
+                                                                const __grid_constant__ CUtensorMap code_map) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Pass2RecSmem<K> &sm = *reinterpret_cast<Pass2RecSmem<K> *>(smem_raw);
+    const int H = p.cc.H, W = p.cc.W;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int n = blockIdx.z;
+    const int bt = (n * p.tiles_y + blockIdx.y) * p.tiles_x + blockIdx.x;
+    const int ty0 = blockIdx.y * kTH, tx0 = blockIdx.x * kTW;
+    const int64_t img_px = (int64_t)n * H * W;
+    const bool want_rgb = p.d_src_rgb != nullptr && p.d_out_rgb != nullptr;
+    const bool want_lay = p.d_src_lay != nullptr && p.d_out_lay != nullptr;
+
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        unsigned bytes = (unsigned)(sizeof(sm.frac) + sizeof(sm.code));
+        if (want_lay) bytes += (unsigned)sizeof(sm.lay);
+        if (want_rgb) bytes += (unsigned)sizeof(sm.rgb);
+        mbar_expect_tx(&sm.bar, bytes);
+        tma_load_3d(sm.code, &code_map, &sm.bar, tx0 - kQX2, ty0 - kRMax, n);
+        tma_load_3d(sm.frac, &frac_map, &sm.bar, (tx0 - kQX2) * 2, ty0 - kRMax, n);
+        if (want_lay) tma_load_4d(sm.lay, &lay_map, &sm.bar, 0, tx0 - kRMax, ty0 - kRMax, n);
+        if (want_rgb) tma_load_3d(sm.rgb, &rgb_map, &sm.bar, (tx0 - kQX2) * 3, ty0 - kRMax, n);
+    }
+    const uint32_t tile_far = p.far_acc ? __ldg(p.tile_flags + bt) : 0u;   // consumed at the very end: issue early
+    const int r = near_radius(p, n, blockIdx.y, blockIdx.x);
+    __syncthreads();          // the barrier object is initialised
+    mbar_wait(&sm.bar, 0);    // the four windows have landed
+
+    // ---- one thread per source pixel: fixed-order gather ----
+    const int ty = tid / kTW, tx = tid - ty * kTW;
+    const int sy = ty0 + ty, sx = tx0 + tx;
+    const bool live = sy < H && sx < W;
+    float acc_l[K], acc_r[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc_l[k] = 0.f;
+    for (int dy = live ? -r : r + 1; dy <= r; ++dy) {
+        // candidate output pixel (sx + ddx, sy + dy), ddx = j - r, sits at window cell (ty + kRMax + dy, tx + kQX2 + ddx).
+        // With its record code = (x0 - x + 8) | (y0 - y + 8) << 16,
+        //   e = ((8 - ddx) | (8 - dy) << 16) - code = (sx - x0) | (sy - y0) << 16:
+        // a hit iff both differences are 0 (west / north tap) or 1 (east / south tap); any other difference
+        // (incl. borrows, and code 0) leaves a bit outside {0, 16}.
+        const int crow = (ty + kRMax + dy) * kQW2 + tx + kQX2 - r;
+        const uint32_t c0 = (uint32_t)(8 + r) | ((uint32_t)(8 - dy) << 16);
+        uint32_t ev[2 * kRMax + 1];
+#pragma unroll
+        for (int j = 0; j < 2 * kRMax + 1; ++j) ev[j] = (j <= 2 * r) ? (c0 - (uint32_t)j) - sm.code[crow + j] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < 2 * kRMax + 1; ++j) {
+            const uint32_t e = ev[j];
+            if (e & 0xFFFEFFFEu) continue;
+            const int cell = crow + j;
+            const float2 f = sm.frac[cell];
+            // east/south = frac, west/north = 1 - frac: bit-identical to the forward's (x0 + 1) - ix for every
+            // in-image tap (both are exact for x0 >= 1, and the same expression for x0 == 0)
+            const float wx = (e & 1u) ? f.x : __fsub_rn(1.0f, f.x);
+            const float wy = (e >> 16) ? f.y : __fsub_rn(1.0f, f.y);
+            const float w = __fmul_rn(wx, wy);
+            if (want_lay) {
+                float v[K];
+                load_px_smem<float, K>(sm.lay + (size_t)((ty + kRMax + dy) * kQW + tx + kRMax - r + j) * K, v);
+                fma2_bcast<K>(acc_l, v, w);
+            }
+            if (want_rgb) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc_r[c] = fmaf(w, sm.rgb[cell * 3 + c], acc_r[c]);
+            }
+        }
+    }
+    const int64_t so = img_px + (int64_t)sy * W + sx;
+    if (live && tile_far) {
+        const double inv = 1.0 / far_scale(p.hdr, p.HW);
+        const long long *fa = p.far_acc + so * (3 + K);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc_r[c] += (float)((double)fa[c] * inv);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc_l[k] += (float)((double)fa[3 + k] * inv);
+    }
+    if (live && want_rgb) store_px<T, 3>(reinterpret_cast<T *>(p.d_src_rgb) + so * 3, acc_r);
+    if (want_lay) {
+        // transpose through shared memory: each warp writes its tile row (32 px x K, contiguous in HBM)
+        // as consecutive 16-byte words
+        __syncthreads();                                   // all gathers done: the d_out staging can be reused
+        T *s_out = reinterpret_cast<T *>(sm.lay);          // [kThreads][K]
+        if (live) store_px<T, K>(s_out + (size_t)tid * K, acc_l);
+        __syncwarp();
+        const int sy_w = ty0 + wid;                        // warp w owns tile row w (kTW == 32)
+        if (sy_w < H) {
+            const int npx = min(kTW, W - tx0);
+            T *grow = reinterpret_cast<T *>(p.d_src_lay) + (img_px + (int64_t)sy_w * W + tx0) * K;
+            const T *srow = s_out + (size_t)wid * kTW * K;
+            if constexpr ((K * sizeof(T)) % 16 == 0) {
+                const int nvec = npx * (int)(K * sizeof(T) / 16);
+                for (int i = lane; i < nvec; i += 32)
+                    reinterpret_cast<uint4 *>(grow)[i] = reinterpret_cast<const uint4 *>(srow)[i];
+            } else {
+                for (int i = lane; i < npx * K; i += 32) grow[i] = srow[i];
+            }
+        }
+    }
+}
+
+// Tap records for the pass-1 organisations that do not write them themselves (everything except
+// lay_tile_kernel): one thread per output pixel.
+__global__ void __launch_bounds__(256) tap_records_kernel(CoordCfg cc, int64_t P, int64_t HW, int pitch,
+                                                          const float2 *__restrict__ coords, uint32_t *rec_code, float2 *rec_frac) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int64_t n = i / HW, rem = i - n * HW;
+    const int y = (int)(rem / cc.W), x = (int)(rem - (int64_t)y * cc.W);
+    const Taps t = make_taps(cc, __ldg(coords + i), y, x);
+    const int64_t ro = (n * cc.H + y) * pitch + x;
+    rec_code[ro] = tap_cell_code(cc, t, y, x);
+    rec_frac[ro] = make_float2(t.ix - t.fx0, t.iy - t.fy0);
+}
+
 // ---- far path: zero the fixed-point accumulators of the flagged source tiles only ----
 template <int K>
 __global__ void __launch_bounds__(kThreads) far_zero_kernel(const Pass2Params p) {
@@ -288,7 +441,7 @@ __global__ void far_scatter_kernel(const Pass2Params p) {
         float d;
         if (c < 3) {
             if (!p.d_out_rgb) continue;
-            d = __ldg(p.d_out_rgb + i * 3 + c);
+            d = __ldg(p.d_out_rgb + ((n * H + y) * p.pitch + x) * 3 + c);
         } else {
             if (!p.d_out_lay) continue;
             d = __ldg(p.d_out_lay + i * K + (c - 3));

@@ -47,7 +47,8 @@ struct RgbParams {
     float c_l1, c_gd, c_ssim;       // gradient scales (0 when the term is masked off)
     uint32_t terms;
     float *d_coords;                // [P][2] rgb part of d(loss)/d(coords); the layout kernel that follows adds its own (nullable)
-    float *d_out_rgb;               // [P][3] fp32 staging for pass 2 (nullable)
+    float *d_out_rgb;               // [N][H][pitch][3] fp32 staging for pass 2 (nullable)
+    int pitch;
     float *partials;                // [n_warps][kRgbSlots]
     WsHeader *hdr;
 };
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                 }
                 if (out_lane) {
                     const int64_t o = img + (int64_t)(t - 2) * W + x;
-                    if (p.d_out_rgb) store_px<float, 3>(p.d_out_rgb + o * 3, dr);
+                    if (p.d_out_rgb) store_px<float, 3>(p.d_out_rgb + (((int64_t)n * H + (t - 2)) * p.pitch + x) * 3, dr);
                     if (p.d_coords) reinterpret_cast<float2 *>(p.d_coords)[o] = make_float2(gx, gy);
                 }
             }

@@ -42,6 +42,8 @@ class WarpLossConfig:
     tile_kernels: bool = False            # evaluate ALL of pass 1 in the first (non-persistent) 32x8 tile kernel
     layout_kernel: str = "tile2"          # layout half of pass 1: 'tile2' persistent double-buffered tile kernel (default),
                                           # 'strip' per-warp TMA row ring, 'tile' first tile kernel
+    pass2_records: bool = True            # pass 2 gathers from the tap records pass 1 wrote (all staging by TMA);
+                                          # False: it re-derives them from the coordinates (first pass-2 kernel)
     term_mask: int = 0                    # 0 = all terms
     class_weight: Optional[torch.Tensor] = None   # per-class CE weights (K floats on the device)
     ce_norm: str = "torch"                # 'torch' (weighted mean) | 'count' (sum / n_known, src/models/simple.py:56-59)
@@ -107,6 +109,8 @@ def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
     flags = (_cabi.FLAG_NO_FAR_PATH if cfg.assume_near else 0) | (0 if cfg.use_tma else _cabi.FLAG_NO_TMA)
     if cfg.tile_kernels:
         flags |= _cabi.FLAG_TILE_RGB | _cabi.FLAG_TILE_LAYOUT
+    if not cfg.pass2_records:
+        flags |= _cabi.FLAG_PASS2_COORDS
     if cfg.layout_kernel not in ("tile2", "strip", "tile"):
         raise VlgError(f"layout_kernel must be 'tile2', 'strip' or 'tile', not {cfg.layout_kernel!r}")
     flags |= {"tile2": 0, "strip": _cabi.FLAG_STRIP_LAYOUT, "tile": _cabi.FLAG_TILE_LAYOUT}[cfg.layout_kernel]
