@@ -154,6 +154,19 @@ int vlg_colorize(const vlg_problem_t *prob, const void *layout, const int64_t *l
 int vlg_one_hot(const vlg_problem_t *prob, const int64_t *label_i64, const float *label_f32,
                 void *out_layout, void *workspace, void *stream);
 
+/* Boundary fusion around the path: per-channel affine renormalisation of rgb frames,
+ * horizontal flip and NCHW -> NHWC re-layout in one pass; bit-identical to the reference's torch ops.
+ *   denormalize == 0:  out = (in - a[c]) / b[c]   src/trainer.py:193-195 (img_mean_arr, img_std_arr), :212,:324
+ *   denormalize != 0:  out = in * b[c] + a[c]     src/trainer.py:215
+ *   flip_w: torch.flip(frame, [3]) and torch.flip(seg3, [2])   src/trainer.py:200-206
+ *   in_rgb  fp32, [N,3,H,W] contiguous (in_is_nchw != 0, what the DataLoader hands) or [N,H,W,3]
+ *   a3, b3  HOST pointers to 3 floats each (passed to the kernel by value)
+ *   out_rgb [N,H,W,3] of the problem's dtype;  label_in/label_out [N,H,W] i64 (nullable pair)
+ * prob->K, padding, coord_mode are ignored. */
+int vlg_frame_affine(const vlg_problem_t *prob, const float *in_rgb, int32_t in_is_nchw, const float *a3,
+                     const float *b3, int32_t denormalize, int32_t flip_w, void *out_rgb,
+                     const int64_t *label_in, int64_t *label_out, void *stream);
+
 /* Pass 1 of the fused op: warp + all loss terms + d(loss)/d(warped) + d(loss)/d(coords) in one
  * kernel.  Gradients are for an upstream grad of 1.0 (see vlg_scale_grads).
  *   tgt_rgb [N,H,W,3], tgt_label [N,H,W] i64

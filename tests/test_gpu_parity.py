@@ -563,3 +563,27 @@ def test_one_hot_layout_matches_reference_encoding():
     d = _make_case(1, 40, 64, 20, 1.0, seed=4, layout="onehot")
     lay = vlg_b200.one_hot_layout(d["src_layout"].argmax(1).to(DEV), 20)
     assert torch.equal(lay.cpu(), d["src_layout"])
+
+
+def test_prepare_frames_matches_reference_renorm_and_flip():
+    """Per-channel renorm `(x - mean) / std` (src/trainer.py:193-195,212,324), its inverse (:215) and the flip
+    augmentation (:200-206) fused with the NCHW -> NHWC re-layout: bit-identical to the torch expressions,
+    for plain-contiguous and channels_last inputs, vectorised (W % 4 == 0) and scalar widths."""
+    g = torch.Generator().manual_seed(5)
+    for (N, H, W) in ((2, 16, 32), (1, 13, 37), (3, 8, 1242 // 6)):
+        frames = torch.rand(N, 3, H, W, generator=g)
+        labels = torch.randint(0, 20, (N, H, W), generator=g)
+        for flip in (False, True):
+            for denorm in (False, True):
+                want, want_lab = TO.renorm_frames(frames, flip=flip, denormalize=denorm, labels=labels)
+                for src in (frames.to(DEV), _cl(frames)):
+                    got, got_lab = vlg_b200.prepare_frames(src, flip=flip, denormalize=denorm, labels=labels.to(DEV))
+                    assert got.is_contiguous(memory_format=torch.channels_last) and got.shape == want.shape
+                    assert torch.equal(got.cpu(), want), (N, H, W, flip, denorm)
+                    assert torch.equal(got_lab.cpu(), want_lab)
+        # generator-output normalisation constants (src/trainer.py:120-121,212) and bf16 output
+        want = TO.renorm_frames(frames, vlg_b200.ops.OUT_MEAN, vlg_b200.ops.OUT_STD)
+        got = vlg_b200.prepare_frames(frames.to(DEV), vlg_b200.ops.OUT_MEAN, vlg_b200.ops.OUT_STD)
+        assert torch.equal(got.cpu(), want)
+        got16 = vlg_b200.prepare_frames(frames.to(DEV), dtype=torch.bfloat16)
+        assert torch.equal(got16.cpu(), TO.renorm_frames(frames).to(torch.bfloat16))

@@ -110,3 +110,20 @@ def test_c_oracle_backward_close_to_torch(golden):
     ds, dg = CO.warp_bwd(g["src_layout"], g["grid"], go.numpy(), g["padding"])
     assert np.abs(ds - src.grad.numpy()).max() <= 1e-5 * np.abs(ds).max()
     assert np.abs(dg - grid.grad.numpy()).max() <= 1e-5 * np.abs(dg).max()
+
+
+def test_renorm_oracle_follows_trainer_expressions():
+    """oracle.renorm_frames restates src/trainer.py:122-123,193-195,200-206,215 -- the tensors are built exactly
+    as the trainer builds them ([None,:,None,None] broadcasts of the same constants)."""
+    import torch
+    from oracle import torch_oracle as TO
+    g = torch.Generator().manual_seed(2)
+    frame = torch.rand(2, 3, 9, 14, generator=g)
+    seg = torch.randint(0, 20, (2, 9, 14), generator=g)
+    img_std_arr = torch.tensor([0.229, 0.224, 0.225])[None, :, None, None]
+    img_mean_arr = torch.tensor([0.485, 0.456, 0.406])[None, :, None, None]
+    want = (frame - img_mean_arr) / img_std_arr
+    assert torch.equal(TO.renorm_frames(frame), want)
+    out, lab = TO.renorm_frames(frame, flip=True, labels=seg)
+    assert torch.equal(out, torch.flip(want, [3])) and torch.equal(lab, torch.flip(seg, [2]))
+    assert torch.equal(TO.renorm_frames(want, denormalize=True), want * img_std_arr + img_mean_arr)

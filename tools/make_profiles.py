@@ -86,8 +86,8 @@ if os.path.exists(rep):
                     os.path.join(ROOT, "video-layout-generation_b200", "csrc", "vlg_api.cu")], check=True)
     open(sas, "w").write(run(["nvdisasm", "-g", "-c", cub]))
     with open(os.path.join(P, f"{tag}_ncu_source_hotspots.txt"), "w") as f:
-        for kre, ksub, mainf in (("rgb_strip", "rgb_strip_kernelIfLb1ELb1", "vlg_rgb.cuh"), ("lay_tile", "lay_tile_kernelILi20ELb1", "vlg_laytile.cuh"),
-                                 ("pass2_kernel", "pass2_kernelIfLi20E", "vlg_pass2.cuh")):
+        for kre, ksub, mainf in (("rgb_strip", "rgb_strip_kernelIfLb1ELb1", "vlg_rgb.cuh"), ("lay_tile", "lay_tile_kernelIfLi20ELb1ELb0", "vlg_laytile.cuh"),
+                                 ("pass2_rec_kernel", "pass2_rec_kernelIfLi20E", "vlg_pass2.cuh")):
             src = os.path.join(G, f"{tag}_{kre}_src.csv")
             open(src, "w").write(run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}"]))
             f.write(f"######## {kre}\n")

@@ -12,6 +12,7 @@
 #include "vlg_rgb.cuh"
 #include "vlg_lay.cuh"
 #include "vlg_laytile.cuh"
+#include "vlg_frames.cuh"
 
 using namespace vlg;
 
@@ -617,6 +618,32 @@ static int dispatch_lay(const vlg_problem_t *prob, const LayParams &lp, const CU
     return fail(VLG_ERR_UNSUPPORTED, "layout strip kernel: K not compiled in");
 }
 
+// Side stream + fork/join events of the calling thread (created once per thread and device).  Used to run the
+// label count next to the rgb strip kernel, which does not need it; works under stream capture too (the side
+// stream joins the capture through the fork event and is joined back before the layout kernel).
+struct SideLane {
+    int dev = -1;
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideLane *side_lane() {
+    static thread_local SideLane lane;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (lane.dev != dev) {
+        SideLane nl;
+        if (cudaStreamCreateWithFlags(&nl.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&nl.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&nl.join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        nl.dev = dev;
+        lane = nl;   // a lane of another device (if any) is left to the driver: a thread rarely changes device
+    }
+    return &lane;
+}
+
 static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, const void *src_layout,
                      const float *coords, const void *tgt_rgb, const int64_t *tgt_label, float *d_coords,
                      void *d_out_rgb, void *d_out_lay, bool need_grad, int64_t *out_argmax, float *fused_loss_out,
@@ -629,11 +656,21 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     const int64_t P = prob->N * prob->H * prob->W;
     const bool has_lay = src_layout && tgt_label;
     const bool rgb_strips = warp && src_rgb && tgt_rgb && !(prob->flags & VLG_FLAG_TILE_RGB);
+    bool join_count = false;
+    SideLane *lane = nullptr;
     if (has_lay) {
+        // the rgb strip kernel does not need the label count: fork it onto the side stream, join before the layout kernel
+        cudaStream_t cst = st;
+        if (rgb_strips && (lane = side_lane()) != nullptr && cudaEventRecord(lane->fork, st) == cudaSuccess &&
+            cudaStreamWaitEvent(lane->s, lane->fork, 0) == cudaSuccess) {
+            cst = lane->s;
+            join_count = true;
+        }
         const int blocks = (int)((P + 256 * 16 - 1) / (256 * 16));
-        count_valid_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(tgt_label, P, prob->ignore_index, (int)prob->K,
-                                                                     prob->ce_class_weight, hdr);
+        count_valid_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, cst>>>(tgt_label, P, prob->ignore_index, (int)prob->K,
+                                                                      prob->ce_class_weight, hdr);
         int rc = check_launch("count_valid_kernel");
+        if (join_count && cudaEventRecord(lane->join, lane->s) != cudaSuccess) return fail(VLG_ERR_CUDA, "side stream join record failed");
         if (rc) return rc;
     }
     const double Ng = (double)(prob->global_N ? prob->global_N : prob->N);
@@ -695,6 +732,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
         pp.src_rgb = nullptr; pp.tgt_rgb = nullptr; pp.d_out_rgb = nullptr;
         pp.accum_dcoords = 1;
     }
+    if (join_count && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return fail(VLG_ERR_CUDA, "side stream join failed");
     int rc = VLG_OK;
     bool lay_done = false;
     if (warp && has_lay && prob->K % 4 == 0 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_TILE_LAYOUT))) {
@@ -747,6 +785,24 @@ static int launch_colorize(int64_t P, const void *layout, const int64_t *label, 
     colorize_kernel<T, K><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, (const T *)layout, label, lut, (T *)out_rgb,
                                                                       out_label, nullptr);
     return check_launch("colorize_kernel");
+}
+
+template <typename T>
+static int launch_frame_affine(const vlg_problem_t *prob, const FrameAffine &fa, const float *in, bool nchw, int flip, void *out, cudaStream_t st) {
+    const int64_t P = prob->N * prob->H * prob->W;
+    const int H = (int)prob->H, W = (int)prob->W;
+    const bool vec = W % 4 == 0 && ((uintptr_t)in) % 16 == 0 && ((uintptr_t)out) % 16 == 0;
+    if (vec) {
+        const int64_t groups = P / 4;
+        const unsigned blocks = (unsigned)((groups + 255) / 256);
+        if (nchw) frame_affine_vec4_kernel<T, true><<<blocks, 256, 0, st>>>(fa, groups, H, W, flip, in, (T *)out);
+        else frame_affine_vec4_kernel<T, false><<<blocks, 256, 0, st>>>(fa, groups, H, W, flip, in, (T *)out);
+    } else {
+        const unsigned blocks = (unsigned)((P + 255) / 256);
+        if (nchw) frame_affine_px_kernel<T, true><<<blocks, 256, 0, st>>>(fa, P, H, W, flip, in, (T *)out);
+        else frame_affine_px_kernel<T, false><<<blocks, 256, 0, st>>>(fa, P, H, W, flip, in, (T *)out);
+    }
+    return check_launch("frame_affine_kernel");
 }
 
 // ------------------------------------------------------------------ exported C ABI
@@ -926,6 +982,39 @@ int vlg_pixel_loss_fwd_bwd(const vlg_problem_t *prob, const void *out_rgb, const
     if ((logits == nullptr) != (tgt_label == nullptr)) return fail(VLG_ERR_ARG, "logits and tgt_label go together");
     rc = run_pass1(prob, false, out_rgb, logits, nullptr, tgt_rgb, tgt_label, nullptr, d_out_rgb, d_logits,
                    d_out_rgb != nullptr || d_logits != nullptr, out_argmax, loss_out, workspace, L, (cudaStream_t)stream);
+    return rc;
+}
+
+int vlg_frame_affine(const vlg_problem_t *prob, const float *in_rgb, int32_t in_is_nchw, const float *a3, const float *b3,
+                     int32_t denormalize, int32_t flip_w, void *out_rgb, const int64_t *label_in, int64_t *label_out,
+                     void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if ((in_rgb == nullptr) != (out_rgb == nullptr)) return fail(VLG_ERR_ARG, "in_rgb and out_rgb go together");
+    if ((label_in == nullptr) != (label_out == nullptr)) return fail(VLG_ERR_ARG, "label_in and label_out go together");
+    if (in_rgb && (!a3 || !b3)) return fail(VLG_ERR_ARG, "a3 / b3 (3 host floats each) are required");
+    if (in_rgb && (const void *)in_rgb == (const void *)out_rgb && (flip_w || in_is_nchw))
+        return fail(VLG_ERR_ARG, "in-place only without flip and re-layout");
+    if (label_in && label_in == label_out) return fail(VLG_ERR_ARG, "labels cannot be flipped in place");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_rgb) {
+        FrameAffine fa;
+        for (int c = 0; c < 3; ++c) { fa.a[c] = a3[c]; fa.b[c] = b3[c]; }
+        fa.denorm = denormalize ? 1 : 0;
+        rc = prob->dtype == VLG_F32 ? launch_frame_affine<float>(prob, fa, in_rgb, in_is_nchw != 0, flip_w ? 1 : 0, out_rgb, st)
+                                    : launch_frame_affine<__nv_bfloat16>(prob, fa, in_rgb, in_is_nchw != 0, flip_w ? 1 : 0, out_rgb, st);
+        if (rc) return rc;
+    }
+    if (label_in) {
+        const int64_t P = prob->N * prob->H * prob->W;
+        if (flip_w) {
+            flip_labels_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, (int)prob->W, label_in, label_out);
+            rc = check_launch("flip_labels_kernel");
+        } else {
+            cudaError_t e = cudaMemcpyAsync(label_out, label_in, (size_t)P * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) rc = fail(VLG_ERR_CUDA, "label copy: %s", cudaGetErrorString(e));
+        }
+    }
     return rc;
 }
 

@@ -240,6 +240,43 @@ def one_hot_layout(seg: torch.Tensor, n_classes: int = 20, dtype: torch.dtype = 
     return out
 
 
+# src/trainer.py:120-123
+IMG_MEAN, IMG_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)          # img_mean_arr, img_std_arr
+OUT_MEAN, OUT_STD = (-0.03, -0.088, -0.188), (0.448, 0.448, 0.450)        # mean_arr, std_arr
+
+
+@torch.no_grad()
+def prepare_frames(frames: torch.Tensor, mean=IMG_MEAN, std=IMG_STD, *, flip: bool = False, denormalize: bool = False,
+                   labels: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.float32):
+    """Per-channel renormalisation (+ optional horizontal flip and NCHW -> NHWC re-layout) in one pass.
+
+    normalise   `(frames - mean[None,:,None,None]) / std[None,:,None,None]`   src/trainer.py:193-195,212,324
+    denormalize `frames * std + mean`                                          src/trainer.py:215
+    flip        `torch.flip(frames, [3])`, `torch.flip(labels, [2])`           src/trainer.py:200-206
+    `frames` is fp32 [N,3,H,W], plain-contiguous (what the DataLoader hands) or channels_last; the result is an
+    NCHW-logical tensor in NHWC storage of `dtype`, bit-identical to the torch expressions above.  With `labels`
+    ([N,H,W] int64) returns (frames, labels)."""
+    _require_cuda(frames, labels)
+    if frames.dim() != 4 or frames.shape[1] != 3 or frames.dtype != torch.float32:
+        raise VlgError("prepare_frames expects float32 frames of shape [N,3,H,W]")
+    N, _, H, W = frames.shape
+    nhwc = all(frames.shape[d] == 1 or frames.stride(d) == _nhwc_strides(frames.shape)[d] for d in range(4))
+    if not nhwc:
+        frames = frames.contiguous()
+    prob = _problem(N, H, W, 20, dtype, WarpLossConfig())
+    out = empty_nhwc((N, 3, H, W), dtype, frames.device)
+    a3, b3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    lab_out = None
+    if labels is not None:
+        if labels.dtype != torch.int64 or tuple(labels.shape) != (N, H, W):
+            raise VlgError(f"labels must be int64 [N,H,W]={N, H, W}")
+        labels = labels.contiguous()
+        lab_out = torch.empty_like(labels)
+    check(_cabi.load().vlg_frame_affine(C.byref(prob), _ptr(frames), int(not nhwc), a3, b3, int(denormalize), int(flip),
+                                        _ptr(out), _ptr(labels), _ptr(lab_out), _stream()))
+    return out if labels is None else (out, lab_out)
+
+
 def rollout(img: torch.Tensor, label: torch.Tensor, flow_fn, steps: int = 5, *, padding_mode: str = "border"):
     """Autoregressive rollout (shape of src/trainer.py:453-476, which runs 8 steps and feeds the
     argmax back): step t warps the previous frame and label map with `flow_fn(t, img, label)`
