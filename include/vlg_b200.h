@@ -178,6 +178,14 @@ int vlg_warp_loss_bwd_out(const vlg_problem_t *prob, const void *src_rgb, const 
                           float *d_coords, int64_t *out_argmax, int with_src_grad,
                           void *workspace, size_t workspace_bytes, void *stream);
 
+/* vlg_warp_loss_bwd_out with the final reduction fused in: the last pass-1 CTA writes loss_out[VLG_LOSS_SLOTS]
+ * (nullable), so the loss vector is complete BEFORE pass 2 starts -- a data-parallel caller issues its one
+ * all-reduce of the loss vector (src/trainer.py:381-386) here and lets it overlap vlg_warp_bwd_src. */
+int vlg_warp_loss_pass1(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout,
+                        const float *coords, const void *tgt_rgb, const int64_t *tgt_label, float *loss_out,
+                        float *d_coords, int64_t *out_argmax, int with_src_grad, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* Pass 2: deterministic source gradient (no float atomics): every source pixel gathers, in a
  * fixed order, the d_out of the output pixels whose bilinear footprint covers it.
  *   d_src_rgb [N,H,W,3], d_src_layout [N,H,W,K] (either nullable) */

@@ -24,7 +24,7 @@ LOSS_L1, LOSS_GD, LOSS_SSIM, LOSS_CE, LOSS_TV, LOSS_TOTAL, LOSS_NVALID, LOSS_MAX
 EXPORTS = [
     "vlg_version", "vlg_last_error", "vlg_workspace_bytes", "vlg_warp_fwd", "vlg_warp_fwd_labels", "vlg_colorize", "vlg_one_hot",
     "vlg_frame_affine",
-    "vlg_warp_loss_bwd_out",
+    "vlg_warp_loss_bwd_out", "vlg_warp_loss_pass1",
     "vlg_warp_bwd_src", "vlg_reduce_partials", "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd",
     "vlg_scale_grads", "vlg_read_status", "vlg_launch_count",
 ]
@@ -87,6 +87,8 @@ def load(build_if_missing: bool = True):
     lib.vlg_frame_affine.argtypes = [P, f32p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_int32, vp, i64p, i64p, vp]
     lib.vlg_frame_affine.restype = C.c_int
     lib.vlg_warp_loss_bwd_out.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, i64p, C.c_int, vp, C.c_size_t, vp]
+    lib.vlg_warp_loss_pass1.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, f32p, i64p, C.c_int, vp, C.c_size_t, vp]
+    lib.vlg_warp_loss_pass1.restype = C.c_int
     lib.vlg_warp_bwd_src.argtypes = [P, f32p, vp, vp, vp, C.c_size_t, vp]
     lib.vlg_reduce_partials.argtypes = [P, f32p, vp, C.c_size_t, vp]
     lib.vlg_warp_loss_fwd_bwd.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, f32p, vp, vp, i64p, vp, C.c_size_t, vp]

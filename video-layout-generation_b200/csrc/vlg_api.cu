@@ -909,6 +909,13 @@ int vlg_warp_loss_bwd_out(const vlg_problem_t *prob, const void *src_rgb, const 
                            nullptr, workspace, workspace_bytes, stream);
 }
 
+int vlg_warp_loss_pass1(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
+                        const void *tgt_rgb, const int64_t *tgt_label, float *loss_out, float *d_coords, int64_t *out_argmax,
+                        int with_src_grad, void *workspace, size_t workspace_bytes, void *stream) {
+    return warp_loss_pass1(prob, src_rgb, src_layout, coords, tgt_rgb, tgt_label, d_coords, out_argmax, with_src_grad,
+                           loss_out, workspace, workspace_bytes, stream);
+}
+
 int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src_rgb, void *d_src_layout,
                      void *workspace, size_t workspace_bytes, void *stream) {
     int rc = check_problem(prob);
