@@ -98,15 +98,6 @@ struct LayWarpSmem {
     int ox[kLR];                           // column origin of the row held by each slot
 };
 
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
-                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 template <typename T, int K, bool GRAD>
 __global__ void __launch_bounds__(kLayThreads, VLG_LAY_MIN_BLOCKS) lay_strip_kernel(const LayParams p,
                                                                                    const __grid_constant__ CUtensorMap lay_map) {

@@ -149,6 +149,16 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// bulk shared -> global store (one instruction per contiguous run) and its bookkeeping
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // sampling coordinates from raw coords + the smem base-grid table
 __device__ __forceinline__ float2 source_xy(const CoordCfg &cc, float2 c, float bx, float by, float &mx, float &my) {
     float gx = c.x, gy = c.y;

@@ -366,13 +366,18 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Param
         __syncthreads();                                   // all gathers done: the d_out staging can be reused
         T *s_out = reinterpret_cast<T *>(sm.lay);          // [kThreads][K]
         if (live) store_px<T, K>(s_out + (size_t)tid * K, acc_l);
+        fence_async_smem();                                // this row leaves through the async proxy
         __syncwarp();
         const int sy_w = ty0 + wid;                        // warp w owns tile row w (kTW == 32)
         if (sy_w < H) {
             const int npx = min(kTW, W - tx0);
             T *grow = reinterpret_cast<T *>(p.d_src_lay) + (img_px + (int64_t)sy_w * W + tx0) * K;
             const T *srow = s_out + (size_t)wid * kTW * K;
-            if constexpr ((K * sizeof(T)) % 16 == 0) {
+            const unsigned row_bytes = (unsigned)(npx * K * (int)sizeof(T));
+            if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(grow) & 15) == 0) {
+                // one bulk shared -> global copy per row instead of 32 lanes x (LDS.128 + STG.128)
+                if (lane == 0) { bulk_store(grow, srow, row_bytes); bulk_store_wait_read(); }
+            } else if constexpr ((K * sizeof(T)) % 16 == 0) {
                 const int nvec = npx * (int)(K * sizeof(T) / 16);
                 for (int i = lane; i < nvec; i += 32)
                     reinterpret_cast<uint4 *>(grow)[i] = reinterpret_cast<const uint4 *>(srow)[i];
