@@ -465,7 +465,7 @@ static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_p
         far_zero_kernel<K><<<148 * 2, kThreads, 0, st>>>(pp);
         int rc = check_launch("far_zero_kernel");
         if (rc) return rc;
-        far_scatter_kernel<K><<<148 * 2, 256, 0, st>>>(pp);
+        far_scatter_kernel<K><<<148 * 4, kThreads, 0, st>>>(pp);
         rc = check_launch("far_scatter_kernel");
         if (rc) return rc;
     }
