@@ -25,7 +25,8 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 
-def run_training(steps=20, warmup=3, batch=16, height=256, width=512, classes=20, seed=1024, lr=2e-4, verbose=False):
+def run_training(steps=20, warmup=3, batch=16, height=256, width=512, classes=20, seed=1024, lr=2e-4, verbose=False,
+                 amp="none"):
     import vlg_b200
     from vlg_b200.producer import FlowGridNet, flow_nhw2
     from vlg_b200 import parallel
@@ -42,6 +43,7 @@ def run_training(steps=20, warmup=3, batch=16, height=256, width=512, classes=20
         dist.init_process_group(backend="nccl", device_id=dev)
         own_pg = True
 
+    torch.backends.cudnn.benchmark = True         # src/main.py:122 does the same
     torch.manual_seed(seed)                       # src/main.py:121 seeds with 1024
     net = FlowGridNet(in_channels=8).to(dev).to(memory_format=torch.channels_last)
     if world > 1:
@@ -59,8 +61,11 @@ def run_training(steps=20, warmup=3, batch=16, height=256, width=512, classes=20
 
     def step():
         opt.zero_grad(set_to_none=True)
-        flow, _ = net(x)
-        loss = crit(frame2, seg2_onehot, flow_nhw2(flow), frame3, seg3)
+        # the producer (library convolutions) may run under bf16 autocast; the flow and everything on the
+        # hand-written path stay fp32
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(amp == "bf16")):
+            flow, _ = net(x)
+        loss = crit(frame2, seg2_onehot, flow_nhw2(flow.float()), frame3, seg3)
         loss.backward()
         opt.step()
         return parallel.sync_loss_vector(crit.last_terms, "reference") if world > 1 else crit.last_terms
@@ -86,7 +91,7 @@ def run_training(steps=20, warmup=3, batch=16, height=256, width=512, classes=20
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     out = {
         "iters_per_s": 1e3 / ms.item(), "ms_per_iter": ms.item(), "n_gpus": world, "global_batch": batch * world,
-        "per_gpu_batch": batch, "resolution": [height, width], "producer": "FlowGridNet 3x6 (32/64/96), fp32, torch/cuDNN",
+        "per_gpu_batch": batch, "resolution": [height, width], "producer": "FlowGridNet 3x6 (32/64/96), %s, torch/cuDNN" % ("bf16 autocast" if amp == "bf16" else "fp32"),
         "loss_first": first, "loss_last": terms[5].item(),
         "params": sum(p.numel() for p in net.parameters()),
     }
@@ -102,8 +107,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (weak scaling)")
     ap.add_argument("--height", type=int, default=256)
     ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--amp", default="none", choices=["none", "bf16"], help="autocast dtype of the torch producer")
     args = ap.parse_args()
-    out, rank = run_training(args.steps, args.warmup, args.batch, args.height, args.width)
+    out, rank = run_training(args.steps, args.warmup, args.batch, args.height, args.width, amp=args.amp)
     if rank == 0:
         print(json.dumps({"metric": "train iters/s", **out}))
 
