@@ -587,3 +587,22 @@ def test_prepare_frames_matches_reference_renorm_and_flip():
         assert torch.equal(got.cpu(), want)
         got16 = vlg_b200.prepare_frames(frames.to(DEV), dtype=torch.bfloat16)
         assert torch.equal(got16.cpu(), TO.renorm_frames(frames).to(torch.bfloat16))
+
+
+def test_forward_warp_matches_oracle_bitwise_all_modes():
+    """vlg_warp_fwd against the oracle (fp32 evaluation of the same inputs, rounded once at the store): warped
+    layout, warped rgb and argmax bit for bit -- both paddings, ragged widths, out-of-image flows, fp32 and
+    bf16, K = 20 and K = 19 (scalar-store fallback)."""
+    for (shape, K, sigma, padding) in (((2, 37, 70), 20, 2.0, "border"), ((1, 19, 33), 20, 40.0, "zeros"),
+                                       ((2, 64, 200), 20, 9.0, "zeros"), ((1, 24, 1242 // 6), 20, 3.0, "border"),
+                                       ((1, 30, 45), 19, 3.0, "zeros")):
+        d = _make_case(*shape, K, sigma, seed=41, layout="soft")
+        for dt in (torch.float32, torch.bfloat16):
+            a, b, f = _cl(d["src_rgb"].to(dt)), _cl(d["src_layout"].to(dt)), d["flow"].to(DEV)
+            o_rgb, o_lay, o_arg = vlg_b200.warp(a, b, f, padding_mode=padding)
+            grid = TO.flow_to_grid(d["flow"])
+            want = TO.warp(d["src_layout"].to(dt).float(), grid, padding_mode=padding).to(dt)
+            assert torch.equal(o_lay.cpu().contiguous(), want.contiguous()), (shape, K, padding, dt)
+            assert torch.equal(o_arg.cpu(), torch.argmax(want.float(), 1)), (shape, K, padding, dt)
+            want_rgb = TO.warp(d["src_rgb"].to(dt).float(), grid, padding_mode=padding).to(dt)
+            assert torch.equal(o_rgb.cpu().contiguous(), want_rgb.contiguous()), (shape, K, padding, dt)

@@ -307,18 +307,23 @@ static int launch_one_hot(int64_t P, const int64_t *lab_i, const float *lab_f, v
     return check_launch("one_hot_kernel");
 }
 
-// forward-only warp (validation / rollout): one thread per output pixel
-template <typename T, int K>
+// forward-only warp (validation / rollout): one thread per output pixel.  A CTA owns 256 CONSECUTIVE pixels, i.e.
+// 256 * K contiguous elements of the warped layout: with BULK they are staged in shared memory and every warp
+// sends its 32 pixels as one bulk shared->global copy -- a thread-per-pixel store of 80-byte pixels costs 20 L1
+// wavefronts per 128-bit store instruction, and the kernel is bound by the LSU data pipe (70 %).
+template <typename T, int K, bool BULK>
 __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, int64_t HW, const T *__restrict__ src_rgb,
                                                        const T *__restrict__ src_lay, const float2 *__restrict__ coords,
                                                        T *out_rgb, T *out_lay, int64_t *out_argmax, int2 *dbg) {
+    __shared__ __align__(128) T s_out[BULK ? 256 * K : 1];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const int64_t n = i / HW, rem = i - n * HW;
+    const bool live = i < P;
+    const int64_t ic = live ? i : P - 1;
+    const int64_t n = ic / HW, rem = ic - n * HW;
     const int y = (int)(rem / cc.W), x = (int)(rem - (int64_t)y * cc.W);
-    const Taps t = make_taps(cc, __ldg(coords + i), y, x);
-    if (dbg) dbg[i] = make_int2((int)t.fx0, (int)t.fy0);
-    if (src_rgb && out_rgb) {
+    const Taps t = make_taps(cc, __ldg(coords + ic), y, x);
+    if (dbg && live) dbg[i] = make_int2((int)t.fx0, (int)t.fy0);
+    if (src_rgb && out_rgb && live) {
         float a[3];
         gather_px<T, 3>(src_rgb + n * HW * 3, cc, t, a);
         store_px<T, 3>(out_rgb + i * 3, a);
@@ -326,8 +331,23 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, i
     if (src_lay && (out_lay || out_argmax)) {
         float z[K];
         gather_px<T, K>(src_lay + n * HW * K, cc, t, z);
-        if (out_lay) store_px<T, K>(out_lay + i * K, z);
-        if (out_argmax) {
+        if (out_lay) {
+            if constexpr (BULK) {
+                const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+                store_px<T, K>(s_out + (size_t)threadIdx.x * K, z);
+                fence_async_smem();
+                __syncwarp();
+                const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + w * 32;     // first pixel of this warp
+                const int64_t npx = P - i0 < 32 ? P - i0 : 32;
+                if (lane == 0 && npx > 0) {
+                    bulk_store(out_lay + i0 * K, s_out + (size_t)w * 32 * K, (unsigned)(npx * K * (int64_t)sizeof(T)));
+                    bulk_store_wait_read();
+                }
+            } else if (live) {
+                store_px<T, K>(out_lay + i * K, z);
+            }
+        }
+        if (out_argmax && live) {
             // argmax is taken on the values as STORED (rounded to T), like torch.argmax on the output
             float m = to_f<T>(from_f<T>(z[0]));
             int best = 0;
@@ -509,9 +529,17 @@ template <typename T, int K>
 static int launch_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
                       void *out_rgb, void *out_layout, int64_t *out_argmax, int32_t *dbg, cudaStream_t st) {
     const int64_t HW = prob->H * prob->W, P = prob->N * HW;
-    warp_fwd_kernel<T, K><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
-        make_cc(prob), P, HW, (const T *)src_rgb, (const T *)src_layout, (const float2 *)coords, (T *)out_rgb,
-        (T *)out_layout, out_argmax, (int2 *)dbg);
+    // bulk shared->global copies need 16-byte multiples: 32-pixel runs of K*sizeof(T) bytes on a 16-byte aligned base
+    const bool bulk = out_layout && (32 * K * sizeof(T)) % 16 == 0 && (K * sizeof(T)) % 8 == 0 && ((uintptr_t)out_layout & 15) == 0 &&
+                      (P % 32 == 0 || (P % 32) * K * sizeof(T) % 16 == 0);
+    if (bulk)
+        warp_fwd_kernel<T, K, true><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
+            make_cc(prob), P, HW, (const T *)src_rgb, (const T *)src_layout, (const float2 *)coords, (T *)out_rgb,
+            (T *)out_layout, out_argmax, (int2 *)dbg);
+    else
+        warp_fwd_kernel<T, K, false><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
+            make_cc(prob), P, HW, (const T *)src_rgb, (const T *)src_layout, (const float2 *)coords, (T *)out_rgb,
+            (T *)out_layout, out_argmax, (int2 *)dbg);
     return check_launch("warp_fwd_kernel");
 }
 
