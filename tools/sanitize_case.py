@@ -28,5 +28,15 @@ for (N, H, W, sigma, far) in ((1, 37, 70, 1.5, 0.0), (2, 24, 45, 6.0, 0.05)):
     img = cl(torch.randn(N, 3, H, W)).requires_grad_(True)
     seg = cl(torch.randn(N, K, H, W)).requires_grad_(True)
     vlg_b200.PixelLosses()(img, t, seg, lab).backward()
+    fr = torch.rand(N, 3, H, W, device=dev)
+    vlg_b200.prepare_frames(fr, flip=True, labels=lab)
+    vlg_b200.prepare_frames(cl(fr.cpu()), denormalize=True, dtype=torch.bfloat16)
+    # bf16 layouts (8-byte-unit TMA map), pass 2 from coordinates, other pass-1 organisations
+    a16, b16 = a.detach().to(torch.bfloat16).requires_grad_(True), b.detach().to(torch.bfloat16).requires_grad_(True)
+    total, _, _ = vlg_b200.warp_loss(a16, b16, f, t.to(torch.bfloat16), lab, vlg_b200.WarpLossConfig(w_tv=0.5))
+    total.backward()
+    for kw in (dict(pass2_records=False), dict(layout_kernel="strip"), dict(tile_kernels=True)):
+        total, _, _ = vlg_b200.warp_loss(a, b, f, t, lab, vlg_b200.WarpLossConfig(w_tv=0.5, **kw))
+        total.backward()
 torch.cuda.synchronize()
 print("sanitize case done", float(total))
