@@ -606,3 +606,85 @@ def test_forward_warp_matches_oracle_bitwise_all_modes():
             assert torch.equal(o_arg.cpu(), torch.argmax(want.float(), 1)), (shape, K, padding, dt)
             want_rgb = TO.warp(d["src_rgb"].to(dt).float(), grid, padding_mode=padding).to(dt)
             assert torch.equal(o_rgb.cpu().contiguous(), want_rgb.contiguous()), (shape, K, padding, dt)
+
+
+def test_full_res_bf16_fwd_bwd_config3_vs_gpu_oracle():
+    """BASELINE.json configs[2] shape (1024x2048, bf16 I/O, fp32 flow), two images: losses and all gradients
+    within the bf16 bar (1e-2) of the oracle evaluated by torch CUDA in fp32 on the SAME bf16-rounded inputs;
+    argmax against the oracle's fp32 layouts wherever the top-2 margin exceeds bf16 rounding; two runs are
+    bitwise identical (no float atomics anywhere)."""
+    N, H, W, K = 2, 1024, 2048, 20
+    d = _make_case(N, H, W, K, 4.0, seed=33, layout="soft")
+    bf = lambda t: t.to(torch.bfloat16)
+    src_rgb, src_lay, tgt = bf(d["src_rgb"]), bf(d["src_layout"]), bf(d["tgt_rgb"])
+    lab = d["tgt_label"].to(DEV)
+    runs = []
+    for _ in range(2):
+        a = _cl(src_rgb).requires_grad_(True)
+        b = _cl(src_lay).requires_grad_(True)
+        f = d["flow"].to(DEV).requires_grad_(True)
+        total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(tgt), lab, vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
+        total.backward()
+        runs.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+    for x, y in zip(*runs):
+        assert torch.equal(x, y)
+    vec, arg, ga, gb, gf = runs[0]
+    ra = src_rgb.float().to(DEV).requires_grad_(True)
+    rb = src_lay.float().to(DEV).requires_grad_(True)
+    rf = d["flow"].to(DEV).requires_grad_(True)
+    ref = TO.warp_loss(ra, rb, rf, tgt.float().to(DEV), lab, w_tv=0.5)
+    ref["total"].backward()
+    want = np.array([ref["terms"][k].item() for k in TERMS])
+    np.testing.assert_allclose(vec.cpu().numpy()[:5].astype(np.float64), want, rtol=1e-2)
+    _assert_close_norm(_nchw(gf), _nchw(rf.grad), 1e-2, "d_flow")
+    _assert_close_norm(_nchw(ga), _nchw(ra.grad), 1e-2, "d_src_rgb")
+    _assert_close_norm(_nchw(gb), _nchw(rb.grad), 1e-2, "d_src_layout")
+    wl = ref["warped_layout"].detach()
+    top2 = wl.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 0.02 * top2[:, 0].abs().clamp_min(1.0)
+    assert clear.float().mean().item() > 0.5
+    assert torch.equal(arg[clear], ref["argmax"][clear])
+
+
+def test_kitti_shape_large_displacement_config5_vs_gpu_oracle():
+    """BASELINE.json configs[4] shape (375x1242: ragged tiles, rows that need the pitched workspace arrays) with
+    large-displacement flow (sigma = 48 px smoothed, 5 % of the pixels uniform over the image): most pixels take
+    the fixed-point far path.  Against the oracle evaluated by torch CUDA: warp and argmax bit-exact, losses
+    1e-5, gradients 2e-5 normwise (torch's own scatter is atomic-ordered); two runs bitwise identical."""
+    N, H, W, K = 2, 375, 1242, 20
+    d = _make_case(N, H, W, K, 48.0, seed=55, layout="soft", far_frac=0.05)
+    flow = d["flow"]
+    lab = d["tgt_label"].to(DEV)
+    runs = []
+    for _ in range(2):
+        a = _cl(d["src_rgb"]).requires_grad_(True)
+        b = _cl(d["src_layout"]).requires_grad_(True)
+        f = flow.to(DEV).requires_grad_(True)
+        total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), lab, vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
+        total.backward()
+        runs.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+    for x, y in zip(*runs):
+        assert torch.equal(x, y)
+    vec, arg, ga, gb, gf = runs[0]
+    assert vec[_cabi.LOSS_MAXDISP].item() > 100.0          # the far path really ran
+
+    def oracle(dt):
+        ra = d["src_rgb"].to(DEV, dt).requires_grad_(True)
+        rb = d["src_layout"].to(DEV, dt).requires_grad_(True)
+        rf = flow.to(DEV).requires_grad_(True)
+        ref = TO.warp_loss(ra, rb, rf, d["tgt_rgb"].to(DEV, dt), lab, w_tv=0.5)
+        ref["total"].backward()
+        return ref, ra.grad, rb.grad, rf.grad
+
+    ref, r_a, r_b, r_f = oracle(torch.float32)
+    want = np.array([ref["terms"][k].item() for k in TERMS])
+    np.testing.assert_allclose(vec.cpu().numpy()[:5].astype(np.float64), want, rtol=RTOL)
+    assert torch.equal(arg, ref["argmax"])
+    o_rgb, o_lay, _ = vlg_b200.warp(a.detach(), b.detach(), f.detach())
+    assert torch.equal(o_lay.contiguous(), ref["warped_layout"].detach().contiguous())
+    assert torch.equal(o_rgb.contiguous(), ref["warped_rgb"].detach().contiguous())
+    _assert_close_norm(_nchw(gf), _nchw(r_f), 2e-5, "d_flow")
+    # border pixels collect thousands of clamped contributions: torch's own fp32 atomic scatter drifts there
+    # (SURVEY Appendix A.10), hence the wider normwise bar for the source gradients
+    _assert_close_norm(_nchw(ga), _nchw(r_a), 5e-5, "d_src_rgb")
+    _assert_close_norm(_nchw(gb), _nchw(r_b), 5e-5, "d_src_layout")
