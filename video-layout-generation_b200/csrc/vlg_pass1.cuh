@@ -149,6 +149,11 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// prefetch of a tensor-map descriptor (hides its fetch behind the barrier set-up)
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+
 // bulk shared -> global store (one instruction per contiguous run) and its bookkeeping
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),

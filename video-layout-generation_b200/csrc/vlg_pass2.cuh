@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Param
     const bool want_lay = p.d_src_lay != nullptr && p.d_out_lay != nullptr;
 
     if (tid == 0) {
+        tma_prefetch_desc(&code_map); tma_prefetch_desc(&frac_map); tma_prefetch_desc(&lay_map); tma_prefetch_desc(&rgb_map);
         mbar_init(&sm.bar, 1);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         unsigned bytes = (unsigned)(sizeof(sm.frac) + sizeof(sm.code));
