@@ -312,7 +312,12 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Param
     mbar_wait(&sm.bar, 0);    // the four windows have landed
 
     // ---- one thread per source pixel: fixed-order gather ----
-    const int ty = tid / kTW, tx = tid - ty * kTW;
+    // A warp owns a compact 8 x 4 PATCH of the tile, not a 32-pixel row: the hit body below runs once per distinct
+    // hit offset among the warp's pixels, and the flow varies less across a patch than along a row (fewer, fuller
+    // bodies).  A quarter-warp is still 8 consecutive pixels of one row, so the 80-byte-pixel fetches stay
+    // conflict-free.
+    const int tx = (wid & 3) * 8 + (lane & 7), ty = (wid >> 2) * 4 + (lane >> 3);
+    static_assert(kTW == 32 && kTH == 8, "patch mapping");
     const int sy = ty0 + ty, sx = tx0 + tx;
     const bool live = sy < H && sx < W;
     float acc_l[K], acc_r[3] = {0.f, 0.f, 0.f};
@@ -366,9 +371,9 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Param
         // as consecutive 16-byte words
         __syncthreads();                                   // all gathers done: the d_out staging can be reused
         T *s_out = reinterpret_cast<T *>(sm.lay);          // [kThreads][K]
-        if (live) store_px<T, K>(s_out + (size_t)tid * K, acc_l);
-        fence_async_smem();                                // this row leaves through the async proxy
-        __syncwarp();
+        if (live) store_px<T, K>(s_out + (size_t)(ty * kTW + tx) * K, acc_l);
+        fence_async_smem();                                // the rows leave through the async proxy
+        __syncthreads();                                   // a row holds pixels of four warps (patch mapping)
         const int sy_w = ty0 + wid;                        // warp w owns tile row w (kTW == 32)
         if (sy_w < H) {
             const int npx = min(kTW, W - tx0);
