@@ -688,3 +688,38 @@ def test_kitti_shape_large_displacement_config5_vs_gpu_oracle():
     # (SURVEY Appendix A.10), hence the wider normwise bar for the source gradients
     _assert_close_norm(_nchw(ga), _nchw(r_a), 5e-5, "d_src_rgb")
     _assert_close_norm(_nchw(gb), _nchw(r_b), 5e-5, "d_src_layout")
+
+
+def test_split_entry_points_equal_the_fused_call():
+    """`vlg_warp_loss_pass1` (pass 1 with the fused loss reduction) followed by `vlg_warp_bwd_src` is what a
+    data-parallel caller uses to put its loss all-reduce between the passes; it must give exactly the fused
+    `vlg_warp_loss_fwd_bwd` result: loss vector and all three gradients bit for bit."""
+    import ctypes as C
+    from vlg_b200 import ops as vops
+    lib = _cabi.load()
+    N, H, W, K = 2, 61, 93, 20
+    d = _make_case(N, H, W, K, 3.0, seed=77, layout="soft", far_frac=0.01)
+    a, b, f = _cl(d["src_rgb"]), _cl(d["src_layout"]), d["flow"].to(DEV)
+    t, lab = _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV)
+    prob = vops._problem(N, H, W, K, torch.float32, vlg_b200.WarpLossConfig(w_tv=0.5))
+    ptr = vops._ptr
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    res = []
+    for split in (False, True):
+        ws = vops._workspace(prob, True, a.device)
+        loss = torch.zeros(_cabi.LOSS_SLOTS, dtype=torch.float32, device=DEV)
+        d_c = torch.empty(N, H, W, 2, dtype=torch.float32, device=DEV)
+        d_a = vops.empty_nhwc((N, 3, H, W), torch.float32, a.device)
+        d_b = vops.empty_nhwc((N, K, H, W), torch.float32, a.device)
+        if split:
+            vops.check(lib.vlg_warp_loss_pass1(C.byref(prob), ptr(a), ptr(b), ptr(f), ptr(t), ptr(lab), ptr(loss), ptr(d_c), None, 1,
+                                               ptr(ws), ws.numel(), sp))
+            vops.check(lib.vlg_warp_bwd_src(C.byref(prob), ptr(f), ptr(d_a), ptr(d_b), ptr(ws), ws.numel(), sp))
+        else:
+            vops.check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), ptr(a), ptr(b), ptr(f), ptr(t), ptr(lab), ptr(loss), ptr(d_c), ptr(d_a),
+                                                 ptr(d_b), None, ptr(ws), ws.numel(), sp))
+        torch.cuda.synchronize()
+        res.append((loss.clone(), d_c.clone(), d_a.clone(), d_b.clone()))
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
+    assert res[0][0][_cabi.LOSS_TOTAL].item() > 0 and res[0][3].abs().max().item() > 0
