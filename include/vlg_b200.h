@@ -52,10 +52,8 @@ extern "C" {
 #define VLG_FLAG_NO_TMA 2u      /* stage the source-layout window with cp.async instead of a TMA tensor map   */
 #define VLG_FLAG_TILE_RGB 4u    /* evaluate the rgb terms in the tile kernel instead of the column-strip kernel */
 #define VLG_FLAG_TILE_LAYOUT 8u /* evaluate the layout terms in the first (non-persistent) tile kernel            */
-#define VLG_FLAG_STRIP_LAYOUT 16u /* evaluate the layout terms in the per-warp row-ring strip kernel instead of the
-                                   * persistent double-buffered tile kernel                                          */
-#define VLG_FLAG_PASS2_COORDS 32u /* pass 2 re-derives the tap cells and weights from the coordinates (pass2_kernel)
-                                   * instead of reading the tap records pass 1 wrote (pass2_rec_kernel)              */
+#define VLG_FLAG_PASS2_COORDS 32u /* pass 2 re-derives the tap cells and weights from the coordinates and scans (pass2_kernel)
+                                   * instead of registering the tap records pass 1 wrote (pass2_rec_kernel)            */
 
 /* term_mask bits */
 #define VLG_TERM_L1 1u

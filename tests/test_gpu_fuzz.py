@@ -10,9 +10,11 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 import vlg_b200
 from vlg_b200 import _cabi
 from oracle import torch_oracle as TO
+from conftest import assert_grad_parity, assert_terms_parity
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+RTOL = 1e-5   # BASELINE.json north_star: losses and gradients within 1e-5 relative in fp32
 
 
 def _cl(t):
@@ -42,26 +44,34 @@ def test_fuzz_warp_loss_against_oracle(N, H, W, K, padding, as_grid, sigma, seed
     w_tv = 0.0 if as_grid else 0.7
     has_ssim = H >= 3 and W >= 3
 
-    # oracle (SSIM is undefined below 3x3: the product reports 0 for it, the reference would raise)
-    a, b, c = (t.clone().requires_grad_(True) for t in (src_rgb, src_lay, coords))
-    grid = c if as_grid else TO.flow_to_grid(c)
-    w_rgb, w_lay = TO.warp(a, grid, padding), TO.warp(b, grid, padding)
-    terms = [TO.l1_loss(w_rgb, tgt_rgb), TO.gradient_loss(w_rgb, tgt_rgb),
-             TO.ssim_loss(w_rgb, tgt_rgb) if has_ssim else torch.zeros(()), TO.cross_entropy(w_lay, label),
-             TO.flow_tv(c) if (not as_grid and H > 1 and W > 1) else torch.zeros(())]
-    total = 40 * terms[0] + 20 * (terms[1] + terms[2]) + 10 * terms[3] + w_tv * terms[4]
-    total.backward()
+    # oracle (SSIM is undefined below 3x3: the product reports 0 for it, the reference would raise), evaluated in
+    # fp32 and -- as the tie-breaker of SURVEY Appendix A.10 -- in fp64 on the SAME fp32 sampling grid
+    def oracle(dt):
+        a, b, c = (t.to(dt).clone().requires_grad_(True) for t in (src_rgb, src_lay, coords))
+        if dt == torch.float32:
+            grid = c if as_grid else TO.flow_to_grid(c)
+        else:   # same fp32 sampling positions (the spec), fp64 accumulation: TO.high_precision_grid
+            g32 = coords if as_grid else TO.flow_to_grid(coords)
+            grid = TO.high_precision_grid(g32, c, 1.0 if as_grid else TO.flow_scale(H, W, torch.float32).to(dt))
+        w_rgb, w_lay = TO.warp(a, grid, padding), TO.warp(b, grid, padding)
+        terms = [TO.l1_loss(w_rgb, tgt_rgb.to(dt)), TO.gradient_loss(w_rgb, tgt_rgb.to(dt)),
+                 TO.ssim_loss(w_rgb, tgt_rgb.to(dt)) if has_ssim else torch.zeros(()), TO.cross_entropy(w_lay, label),
+                 TO.flow_tv(c) if (not as_grid and H > 1 and W > 1) else torch.zeros(())]
+        total = 40 * terms[0] + 20 * (terms[1] + terms[2]) + 10 * terms[3] + w_tv * terms[4]
+        total.backward()
+        return np.array([t.item() for t in terms]), w_lay.detach(), (c.grad, a.grad, b.grad)
+
+    want32, w_lay, g32_ = oracle(torch.float32)
+    want64, _, g64_ = oracle(torch.float64)
 
     ga, gb, gc = _cl(src_rgb).requires_grad_(True), _cl(src_lay).requires_grad_(True), coords.to(DEV).requires_grad_(True)
     cfg = vlg_b200.WarpLossConfig(w_tv=w_tv, padding_mode=padding, coords_are_grid=as_grid, want_argmax=True)
     tot, vec, arg = vlg_b200.warp_loss(ga, gb, gc, _cl(tgt_rgb), label.to(DEV), cfg)
     tot.backward()
 
-    got = vec.cpu().numpy().astype(np.float64)
-    want = np.array([t.item() for t in terms])
-    np.testing.assert_allclose(got[:5], want, rtol=2e-5, atol=1e-6)
-    assert torch.equal(arg.cpu(), torch.argmax(w_lay.detach(), 1))
-    for name, x, r in (("d_coords", gc.grad, c.grad), ("d_src_rgb", ga.grad, a.grad), ("d_src_layout", gb.grad, b.grad)):
-        err = (x.detach().float().cpu().contiguous() - r).abs().max().item()
-        scale = max(r.abs().max().item(), 1e-12)
-        assert err <= 2e-5 * scale, (name, err, scale, (N, H, W, K, padding, as_grid, sigma, seed))
+    case = (N, H, W, K, padding, as_grid, sigma, seed)
+    assert_terms_parity(vec.cpu().numpy()[:5], want32, want64, RTOL)
+    assert torch.equal(arg.cpu(), torch.argmax(w_lay, 1)), case
+    for name, x, r32, r64 in (("d_coords", gc.grad, g32_[0], g64_[0]), ("d_src_rgb", ga.grad, g32_[1], g64_[1]),
+                              ("d_src_layout", gb.grad, g32_[2], g64_[2])):
+        assert_grad_parity(x.detach().float().cpu().contiguous(), r32, r64, RTOL, f"{name} {case}")

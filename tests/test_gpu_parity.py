@@ -4,8 +4,10 @@
  (3) size-independent properties at BASELINE.json's full sizes.
 
 Bars (BASELINE.json north_star): sampling indices and argmax bit-exact; losses and gradients
-within 1e-5 relative in fp32.  For gradient tensors "relative" is normwise:
-max|g - g_ref| <= 1e-5 * max|g_ref| (element-wise relative error is meaningless where terms cancel).
+within 1e-5 relative in fp32 (1e-2 in bf16).  No test in this file asserts a wider bar.  For gradient
+tensors "relative" is evaluated normwise-max AND RMS-relative (conftest.assert_grad_parity; element-wise
+relative error is meaningless where terms cancel), against the fp32 oracle or -- where torch's own
+atomic-ordered fp32 scatter drifts -- the fp64 evaluation of the same oracle.
 """
 import numpy as np
 import pytest
@@ -13,7 +15,7 @@ import torch
 
 import vlg_b200
 from vlg_b200 import _cabi
-from conftest import golden_names, load_golden
+from conftest import assert_grad_parity, assert_terms_parity, golden_names, load_golden
 from oracle import c_oracle as CO
 from oracle import torch_oracle as TO
 
@@ -37,18 +39,27 @@ def _nchw(t):
 
 
 def _assert_close_norm(got, ref, rtol, what):
-    err = np.abs(got - ref).max()
-    scale = np.abs(ref).max()
-    assert err <= rtol * scale + 1e-30, f"{what}: max err {err:.3e} vs {rtol:g} * {scale:.3e}"
+    """Normwise-max AND RMS-relative error of a gradient tensor against one oracle evaluation."""
+    assert_grad_parity(got, ref, None, rtol, what)
 
 
 def _assert_close_either(got, ref32, ref64, rtol, what):
     """torch's own fp32 accumulation drifts by ~1e-5 where thousands of
     contributions meet (border pixels under large displacement); an fp64 evaluation of the same
-    oracle is the tie-breaker.  Pass if within rtol of EITHER."""
-    scale = np.abs(ref64).max()
-    e32, e64 = np.abs(got - ref32).max(), np.abs(got - ref64).max()
-    assert min(e32, e64) <= rtol * scale + 1e-30, f"{what}: err vs fp32 {e32:.3e}, vs fp64 {e64:.3e}, bar {rtol * scale:.3e}"
+    oracle is the tie-breaker.  Pass if within rtol of EITHER (normwise-max and RMS-relative)."""
+    assert_grad_parity(got, ref32, ref64, rtol, what)
+
+
+def _gpu_oracle(d, dtype, w_tv=0.5, padding="border", flow=None, label=None):
+    """The oracle (oracle/torch_oracle.py) evaluated by torch CUDA in `dtype` on the case `d`: returns the dict of
+    TO.warp_loss_fwd_bwd (terms, argmax, warped_*, d_flow, d_src_rgb, d_src_layout), tensors on the device."""
+    dev = lambda t: t.to(DEV)
+    return TO.warp_loss_fwd_bwd(dev(d["src_rgb"]), dev(d["src_layout"]), dev(d["flow"] if flow is None else flow), dev(d["tgt_rgb"]),
+                                dev(d["tgt_label"] if label is None else label), w_tv=w_tv, padding_mode=padding, dtype=dtype)
+
+
+def _terms(ref):
+    return np.array([ref["terms"][k].item() for k in TERMS])
 
 
 def _cfg(g, **kw):
@@ -285,8 +296,9 @@ def test_assume_near_matches_default_path():
 
 # ------------------------------------------------------------------ full-size properties (BASELINE config 2)
 def test_full_size_properties_config2():
-    """16x256x512, K=20 (BASELINE.json configs[1]): compare against the oracle evaluated by torch on
-    the same GPU, plus size-independent properties."""
+    """16x256x512, K=20 (BASELINE.json configs[1]) against the oracle evaluated by torch CUDA on the same
+    GPU in fp32 AND fp64: warp / argmax bit-exact, losses and all three gradients at 1e-5 (normwise-max and
+    RMS-relative), plus size-independent properties."""
     N, H, W, K = 16, 256, 512, 20
     d = _make_case(N, H, W, K, 4.0, seed=1024)
     a = _cl(d["src_rgb"]).requires_grad_(True)
@@ -295,22 +307,16 @@ def test_full_size_properties_config2():
     tgt, lab = _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV)
     total, vec, arg = vlg_b200.warp_loss(a, b, f, tgt, lab, vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
     total.backward()
-    # oracle on the GPU (torch CUDA ops), fp32
-    ra = d["src_rgb"].to(DEV).requires_grad_(True)
-    rb = d["src_layout"].to(DEV).requires_grad_(True)
-    rf = d["flow"].to(DEV).requires_grad_(True)
-    ref = TO.warp_loss(ra, rb, rf, d["tgt_rgb"].to(DEV), lab, w_tv=0.5)
-    ref["total"].backward()
-    got = vec.cpu().numpy().astype(np.float64)
-    want = np.array([ref["terms"][k].item() for k in TERMS])
-    np.testing.assert_allclose(got[:5], want, rtol=RTOL)
+    ref = _gpu_oracle(d, torch.float32)
+    ref64 = _gpu_oracle(d, torch.float64)
+    assert_terms_parity(vec.cpu().numpy()[:5], _terms(ref), _terms(ref64), RTOL)
     o_rgb, o_lay, o_arg = vlg_b200.warp(a.detach(), b.detach(), f.detach())
     assert torch.equal(o_arg, ref["argmax"]) and torch.equal(arg, ref["argmax"])
     assert torch.equal(o_lay.contiguous(), ref["warped_layout"].detach().contiguous())   # bit-exact vs torch CUDA
     assert torch.equal(o_rgb.contiguous(), ref["warped_rgb"].detach().contiguous())
-    _assert_close_norm(_nchw(f.grad), _nchw(rf.grad), RTOL, "d_flow")
-    _assert_close_norm(_nchw(a.grad), _nchw(ra.grad), 2e-5, "d_src_rgb")      # torch's own scatter is atomic-ordered
-    _assert_close_norm(_nchw(b.grad), _nchw(rb.grad), 2e-5, "d_src_layout")
+    assert_grad_parity(f.grad, ref["d_flow"], ref64["d_flow"], RTOL, "d_flow")
+    assert_grad_parity(a.grad, ref["d_src_rgb"], ref64["d_src_rgb"], RTOL, "d_src_rgb")
+    assert_grad_parity(b.grad, ref["d_src_layout"], ref64["d_src_layout"], RTOL, "d_src_layout")
     # properties: one-hot sources warp to a partition of unity; gradient mass is conserved by the
     # transpose (sum of d_src == sum of weights * d_out == d/d(eps) of loss under src += eps)
     s = o_lay.float().sum(1)
@@ -415,6 +421,27 @@ def test_rollout_five_steps_matches_dense_feedback():
         assert torch.equal(imgs[t], img), t
 
 
+def test_rollout_config4_real_shape_matches_dense_feedback():
+    """BASELINE.json configs[3] at the per-GPU shape of the dp8 run (32x512x1024 over 8 GPUs = 4x512x1024 per rank),
+    5 autoregressive steps: label feedback equals the dense argmax -> one-hot -> warp loop of
+    src/trainer.py:460-469 at every step, frames and label maps bit for bit."""
+    K, steps, N, H, W = 20, 5, 4, 512, 1024
+    d = _make_case(N, H, W, K, 4.0, seed=41)
+    flows = [(_make_case(N, H, W, K, 4.0, seed=200 + t)["flow"]).to(DEV) for t in range(steps)]
+    img0, lab0 = _cl(d["src_rgb"]), d["src_layout"].argmax(1).to(DEV)
+    imgs, labs = vlg_b200.rollout(img0, lab0, lambda t, i, l: flows[t], steps=steps)
+    img, lay = img0, _cl(d["src_layout"])
+    for t in range(steps):
+        img, _, arg = vlg_b200.warp(img, lay, flows[t])
+        # the dense loop of the reference, evaluated by torch CUDA on the same inputs
+        r_lay = TO.warp(lay.contiguous(), TO.flow_to_grid(flows[t]))
+        assert torch.equal(torch.argmax(r_lay, 1), arg), t
+        lay = torch.zeros_like(lay).scatter_(1, arg[:, None], 1.0)     # argmax -> one-hot feedback
+        assert torch.equal(labs[t], arg), t
+        assert torch.equal(imgs[t], img), t
+    assert len(labs) == steps and tuple(labs[-1].shape) == (N, H, W)
+
+
 def test_colorize_matches_vis_seg_mask():
     """src/trainer.py:416-427: rgb = color_map[argmax(seg)] / 255, as NCHW float."""
     K = 20
@@ -496,7 +523,7 @@ def test_kernel_organisations_agree():
     (read-once taps, online softmax), the per-warp TMA row ring, or the first tile kernel.  Argmax
     layouts are bit-identical (same FMA chain); losses and gradients, whose sums are associated
     differently, agree well inside the parity bar."""
-    variants = (dict(), dict(layout_kernel="strip"), dict(layout_kernel="tile"), dict(tile_kernels=True))
+    variants = (dict(), dict(layout_kernel="tile"), dict(tile_kernels=True))
     for sigma, padding, shape in ((0.6, "border", (2, 77, 141)), (5.0, "zeros", (2, 77, 141)), (2.0, "border", (1, 19, 33)),
                                   (9.0, "border", (3, 64, 200))):
         d = _make_case(*shape, 20, sigma, seed=17, layout="soft")
@@ -525,7 +552,7 @@ def test_pass2_from_records_matches_pass2_from_coords_bitwise():
     rows), both paddings, far pixels (fixed-point path), bf16 and every pass-1 organisation (lay_tile_kernel
     writes the records itself, the others go through tap_records_kernel)."""
     cases = ((0.6, "border", (2, 77, 141), {}), (5.0, "zeros", (2, 77, 141), {}), (2.0, "border", (1, 19, 33), {}),
-             (30.0, "border", (2, 64, 200), {}), (2.5, "zeros", (1, 40, 250), dict(layout_kernel="strip")),
+             (30.0, "border", (2, 64, 200), {}), (2.5, "zeros", (1, 40, 250), dict(layout_kernel="tile")),
              (2.5, "border", (1, 40, 250), dict(tile_kernels=True)), (1.5, "border", (2, 375 // 5, 1242 // 6), {}))
     for sigma, padding, shape, kw in cases:
         d = _make_case(*shape, 20, sigma, seed=23, layout="soft")
@@ -609,11 +636,12 @@ def test_forward_warp_matches_oracle_bitwise_all_modes():
 
 
 def test_full_res_bf16_fwd_bwd_config3_vs_gpu_oracle():
-    """BASELINE.json configs[2] shape (1024x2048, bf16 I/O, fp32 flow), two images: losses and all gradients
-    within the bf16 bar (1e-2) of the oracle evaluated by torch CUDA in fp32 on the SAME bf16-rounded inputs;
-    argmax against the oracle's fp32 layouts wherever the top-2 margin exceeds bf16 rounding; two runs are
-    bitwise identical (no float atomics anywhere)."""
-    N, H, W, K = 2, 1024, 2048, 20
+    """BASELINE.json configs[2] at its REAL size (8x1024x2048, bf16 I/O, fp32 flow): losses and all gradients
+    within the bf16 bar (1e-2, normwise-max and RMS-relative) of the oracle evaluated by torch CUDA in fp32 on the
+    SAME bf16-rounded inputs; two runs are bitwise identical (no float atomics anywhere).  Argmax: the product
+    takes it on the fp32-accumulated warp of the bf16 layouts, the oracle on ITS fp32 warp of the same inputs --
+    identical arithmetic (Appendix A.6), so the maps must be equal everywhere, not only where the margin is clear."""
+    N, H, W, K = 8, 1024, 2048, 20
     d = _make_case(N, H, W, K, 4.0, seed=33, layout="soft")
     bf = lambda t: t.to(torch.bfloat16)
     src_rgb, src_lay, tgt = bf(d["src_rgb"]), bf(d["src_layout"]), bf(d["tgt_rgb"])
@@ -626,32 +654,28 @@ def test_full_res_bf16_fwd_bwd_config3_vs_gpu_oracle():
         total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(tgt), lab, vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
         total.backward()
         runs.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+        del a, b, f, total
     for x, y in zip(*runs):
         assert torch.equal(x, y)
     vec, arg, ga, gb, gf = runs[0]
-    ra = src_rgb.float().to(DEV).requires_grad_(True)
-    rb = src_lay.float().to(DEV).requires_grad_(True)
-    rf = d["flow"].to(DEV).requires_grad_(True)
-    ref = TO.warp_loss(ra, rb, rf, tgt.float().to(DEV), lab, w_tv=0.5)
-    ref["total"].backward()
-    want = np.array([ref["terms"][k].item() for k in TERMS])
-    np.testing.assert_allclose(vec.cpu().numpy()[:5].astype(np.float64), want, rtol=1e-2)
-    _assert_close_norm(_nchw(gf), _nchw(rf.grad), 1e-2, "d_flow")
-    _assert_close_norm(_nchw(ga), _nchw(ra.grad), 1e-2, "d_src_rgb")
-    _assert_close_norm(_nchw(gb), _nchw(rb.grad), 1e-2, "d_src_layout")
-    wl = ref["warped_layout"].detach()
-    top2 = wl.topk(2, dim=1).values
-    clear = (top2[:, 0] - top2[:, 1]) > 0.02 * top2[:, 0].abs().clamp_min(1.0)
-    assert clear.float().mean().item() > 0.5
-    assert torch.equal(arg[clear], ref["argmax"][clear])
+    del runs
+    d32 = dict(d, src_rgb=src_rgb.float(), src_layout=src_lay.float(), tgt_rgb=tgt.float())
+    ref = _gpu_oracle(d32, torch.float32)
+    np.testing.assert_allclose(vec.cpu().numpy()[:5].astype(np.float64), _terms(ref), rtol=1e-2)
+    assert_grad_parity(gf, ref["d_flow"], None, 1e-2, "d_flow")
+    assert_grad_parity(ga.float(), ref["d_src_rgb"], None, 1e-2, "d_src_rgb")
+    assert_grad_parity(gb.float(), ref["d_src_layout"], None, 1e-2, "d_src_layout")
+    assert torch.equal(arg, ref["argmax"])
 
 
-def test_kitti_shape_large_displacement_config5_vs_gpu_oracle():
-    """BASELINE.json configs[4] shape (375x1242: ragged tiles, rows that need the pitched workspace arrays) with
-    large-displacement flow (sigma = 48 px smoothed, 5 % of the pixels uniform over the image): most pixels take
-    the fixed-point far path.  Against the oracle evaluated by torch CUDA: warp and argmax bit-exact, losses
-    1e-5, gradients 2e-5 normwise (torch's own scatter is atomic-ordered); two runs bitwise identical."""
-    N, H, W, K = 2, 375, 1242, 20
+@pytest.mark.parametrize("B", [1, 2, 64])
+def test_kitti_shape_large_displacement_config5_vs_gpu_oracle(B):
+    """BASELINE.json configs[4] (375x1242: ragged tiles, rows that need the pitched workspace arrays; batch sweep
+    ends 1 and 64 plus B=2) with large-displacement flow (sigma = 48 px smoothed, 5 % of the pixels uniform over the
+    image): most pixels leave the 3-pixel near path.  Against the oracle evaluated by torch CUDA in fp32 and
+    fp64: warp and argmax bit-exact, losses and all gradients at 1e-5 (normwise-max and RMS-relative); two runs
+    bitwise identical."""
+    N, H, W, K = B, 375, 1242, 20
     d = _make_case(N, H, W, K, 48.0, seed=55, layout="soft", far_frac=0.05)
     flow = d["flow"]
     lab = d["tgt_label"].to(DEV)
@@ -663,31 +687,31 @@ def test_kitti_shape_large_displacement_config5_vs_gpu_oracle():
         total, vec, arg = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), lab, vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
         total.backward()
         runs.append((vec.clone(), arg.clone(), a.grad.clone(), b.grad.clone(), f.grad.clone()))
+        if len(runs) == 2:
+            o_rgb, o_lay, _ = vlg_b200.warp(a.detach(), b.detach(), f.detach())
+        del a, b, f, total
     for x, y in zip(*runs):
         assert torch.equal(x, y)
     vec, arg, ga, gb, gf = runs[0]
-    assert vec[_cabi.LOSS_MAXDISP].item() > 100.0          # the far path really ran
+    del runs
+    assert vec[_cabi.LOSS_MAXDISP].item() > 100.0          # the large-displacement machinery really ran
 
-    def oracle(dt):
-        ra = d["src_rgb"].to(DEV, dt).requires_grad_(True)
-        rb = d["src_layout"].to(DEV, dt).requires_grad_(True)
-        rf = flow.to(DEV).requires_grad_(True)
-        ref = TO.warp_loss(ra, rb, rf, d["tgt_rgb"].to(DEV, dt), lab, w_tv=0.5)
-        ref["total"].backward()
-        return ref, ra.grad, rb.grad, rf.grad
-
-    ref, r_a, r_b, r_f = oracle(torch.float32)
-    want = np.array([ref["terms"][k].item() for k in TERMS])
-    np.testing.assert_allclose(vec.cpu().numpy()[:5].astype(np.float64), want, rtol=RTOL)
+    ref = _gpu_oracle(d, torch.float32)
     assert torch.equal(arg, ref["argmax"])
-    o_rgb, o_lay, _ = vlg_b200.warp(a.detach(), b.detach(), f.detach())
     assert torch.equal(o_lay.contiguous(), ref["warped_layout"].detach().contiguous())
     assert torch.equal(o_rgb.contiguous(), ref["warped_rgb"].detach().contiguous())
-    _assert_close_norm(_nchw(gf), _nchw(r_f), 2e-5, "d_flow")
+    del o_lay, o_rgb
+    t32 = _terms(ref)
+    g32 = {k: ref[k].detach().clone() for k in ("d_flow", "d_src_rgb", "d_src_layout")}
+    del ref
+    torch.cuda.empty_cache()
+    ref64 = _gpu_oracle(d, torch.float64)
+    assert_terms_parity(vec.cpu().numpy()[:5], t32, _terms(ref64), RTOL)
     # border pixels collect thousands of clamped contributions: torch's own fp32 atomic scatter drifts there
-    # (SURVEY Appendix A.10), hence the wider normwise bar for the source gradients
-    _assert_close_norm(_nchw(ga), _nchw(r_a), 5e-5, "d_src_rgb")
-    _assert_close_norm(_nchw(gb), _nchw(r_b), 5e-5, "d_src_layout")
+    #  -- the fp64 evaluation of the same oracle settles those
+    assert_grad_parity(gf, g32["d_flow"], ref64["d_flow"], RTOL, "d_flow")
+    assert_grad_parity(ga, g32["d_src_rgb"], ref64["d_src_rgb"], RTOL, "d_src_rgb")
+    assert_grad_parity(gb, g32["d_src_layout"], ref64["d_src_layout"], RTOL, "d_src_layout")
 
 
 def test_split_entry_points_equal_the_fused_call():

@@ -35,7 +35,7 @@ for (N, H, W, sigma, far) in ((1, 37, 70, 1.5, 0.0), (2, 24, 45, 6.0, 0.05)):
     a16, b16 = a.detach().to(torch.bfloat16).requires_grad_(True), b.detach().to(torch.bfloat16).requires_grad_(True)
     total, _, _ = vlg_b200.warp_loss(a16, b16, f, t.to(torch.bfloat16), lab, vlg_b200.WarpLossConfig(w_tv=0.5))
     total.backward()
-    for kw in (dict(pass2_records=False), dict(layout_kernel="strip"), dict(tile_kernels=True)):
+    for kw in (dict(pass2_records=False), dict(layout_kernel="tile"), dict(tile_kernels=True)):
         total, _, _ = vlg_b200.warp_loss(a, b, f, t, lab, vlg_b200.WarpLossConfig(w_tv=0.5, **kw))
         total.backward()
 torch.cuda.synchronize()

@@ -13,7 +13,6 @@ FLAG_NO_FAR_PATH = 1
 FLAG_NO_TMA = 2
 FLAG_TILE_RGB = 4
 FLAG_TILE_LAYOUT = 8
-FLAG_STRIP_LAYOUT = 16
 FLAG_PASS2_COORDS = 32
 TERM_L1, TERM_GD, TERM_SSIM, TERM_CE, TERM_TV, TERM_ALL = 1, 2, 4, 8, 16, 31
 STATUS_BAD_LABEL, STATUS_FAR_TAPS = 1, 2

@@ -10,7 +10,6 @@
 #include "vlg_pass1.cuh"
 #include "vlg_pass2.cuh"
 #include "vlg_rgb.cuh"
-#include "vlg_lay.cuh"
 #include "vlg_laytile.cuh"
 #include "vlg_frames.cuh"
 
@@ -44,6 +43,47 @@ static int check_launch(const char *what) {
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- per-device launch state ----
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy-derived grid sizes belong to a DEVICE, not to the
+// process: a process that drives several GPUs (nn.DataParallel at src/val.py:131, one thread per device, ...) must
+// opt every device in.  Each launcher keeps one slot per device ordinal; the slots are atomics, and setting an
+// attribute twice is harmless, so concurrent first calls need no lock.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    std::atomic<int> v[kMaxDevices];
+    int get(int dev) const { return v[dev].load(std::memory_order_acquire); }
+    void set(int dev, int x) { v[dev].store(x, std::memory_order_release); }
+};
+static int current_device(int *dev) {
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    if (*dev < 0 || *dev >= kMaxDevices) return fail(VLG_ERR_UNSUPPORTED, "device ordinal %d >= %d", *dev, kMaxDevices);
+    return VLG_OK;
+}
+// number of SMs of the current device (148 on a B200; queried, never assumed)
+static int sm_count() {
+    static PerDevice sms;
+    int dev = 0;
+    if (current_device(&dev)) return 148;
+    int n = sms.get(dev);
+    if (!n) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        sms.set(dev, n);
+    }
+    return n;
+}
+// opt a kernel in to `smem` bytes of dynamic shared memory on the current device (once per device and instantiation)
+template <typename Kern>
+static int ensure_smem(PerDevice &done, Kern kern, size_t smem, const char *what) {
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    if (done.get(dev)) return VLG_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+    done.set(dev, 1);
+    return VLG_OK;
+}
 
 static bool k_supported(int64_t K) {
 #define X(k) if (K == k) return true;
@@ -432,13 +472,14 @@ static bool pass2_from_records(const vlg_problem_t *prob) {
 }
 
 // Tensor map of a pitched workspace array [N][H][pitch * epp] of 4-byte elements (epp elements per pixel) with a
-// window of kQW2 x kQH pixels.
+// window of kQW2 x kQH pixels.  The tensor's extent along x is W (not the pitch): the padding columns of a row are
+// never written by pass 1, so they must arrive as the TMA's out-of-bounds zeros like every other cell outside the image.
 static bool make_pitched_map(const vlg_problem_t *prob, const void *base, int64_t pitch, int epp, CUtensorMapDataType dt, CUtensorMap *map) {
     memset(map, 0, sizeof(*map));
     if (((uintptr_t)base) % 16 != 0 || (pitch * epp * 4) % 16 != 0) return false;
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return false;
-    const cuuint64_t gdim[3] = {(cuuint64_t)(pitch * epp), (cuuint64_t)prob->H, (cuuint64_t)prob->N};
+    const cuuint64_t gdim[3] = {(cuuint64_t)(prob->W * epp), (cuuint64_t)prob->H, (cuuint64_t)prob->N};
     const cuuint64_t gstr[2] = {(cuuint64_t)(pitch * epp * 4), (cuuint64_t)(prob->H * pitch * epp * 4)};
     const cuuint32_t box[3] = {(cuuint32_t)(kQW2 * epp), (cuuint32_t)kQH, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
@@ -451,14 +492,9 @@ static int launch_pass1(bool warp, const Pass1Params &pp, const CUtensorMap &lay
     // the staged source window is the last member: the un-warped criteria do not allocate it
     using Smem = Pass1Smem<T, K>;
     const size_t smem_warp = sizeof(Smem), smem_plain = offsetof(Smem, stage);
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pass1_kernel<T, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(pass1_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
-        if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass1): %s", cudaGetErrorString(e));
-        attr_done = true;
-    }
+    static PerDevice attr_warp, attr_plain;  // per instantiation
+    if (int rc = ensure_smem(attr_warp, pass1_kernel<T, K, true>, smem_warp, "pass1")) return rc;
+    if (int rc = ensure_smem(attr_plain, pass1_kernel<T, K, false>, smem_plain, "pass1")) return rc;
     const dim3 grid((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N);
     (void)n_blocks;
     if (warp) pass1_kernel<T, K, true><<<grid, kThreads, smem_warp, st>>>(pp, lay_map);
@@ -482,10 +518,11 @@ template <typename T, int K>
 static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_problem_t *prob, size_t far_words, cudaStream_t st) {
     (void)P; (void)far_words; (void)prob;
     if (pp.far_acc) {   // both exit at once unless pass 1 queued far pixels
-        far_zero_kernel<K><<<148 * 2, kThreads, 0, st>>>(pp);
+        const int sms = sm_count();
+        far_zero_kernel<K><<<sms * 2, kThreads, 0, st>>>(pp);
         int rc = check_launch("far_zero_kernel");
         if (rc) return rc;
-        far_scatter_kernel<K><<<148 * 4, kThreads, 0, st>>>(pp);
+        far_scatter_kernel<K><<<sms * 4, kThreads, 0, st>>>(pp);
         rc = check_launch("far_scatter_kernel");
         if (rc) return rc;
     }
@@ -497,24 +534,16 @@ static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_p
             make_pitched_map(prob, pp.rec_frac, pp.pitch, 2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, &frac_map) &&
             make_pitched_map(prob, pp.rec_code, pp.pitch, 1, CU_TENSOR_MAP_DATA_TYPE_UINT32, &code_map)) {
             constexpr size_t smem_rec = sizeof(Pass2RecSmem<K>);
-            static bool rec_attr_done = false;  // per instantiation
-            if (!rec_attr_done) {
-                cudaError_t e = cudaFuncSetAttribute(pass2_rec_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec);
-                if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass2_rec): %s", cudaGetErrorString(e));
-                rec_attr_done = true;
-            }
+            static PerDevice rec_attr;  // per instantiation
+            if (int rc = ensure_smem(rec_attr, pass2_rec_kernel<T, K>, smem_rec, "pass2_rec")) return rc;
             pass2_rec_kernel<T, K><<<dim3((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N), kThreads, smem_rec, st>>>(
                 pp, lay_map, rgb_map, frac_map, code_map);
             return check_launch("pass2_rec_kernel");
         }
     }
     constexpr size_t smem = pass2_smem_bytes<K>();
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pass2_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaFuncSetAttribute(pass2): %s", cudaGetErrorString(e));
-        attr_done = true;
-    }
+    static PerDevice attr;  // per instantiation
+    if (int rc = ensure_smem(attr, pass2_kernel<T, K>, smem, "pass2")) return rc;
     (void)n_blocks;
     // the fp32 d_out staging buffer as a [N][H][W][K] tensor with a kQW x kQH window box
     CUtensorMap dout_map;
@@ -547,14 +576,16 @@ static int launch_fwd(const vlg_problem_t *prob, const void *src_rgb, const void
 // contiguous run of (image, strip, row).
 template <typename T>
 static int launch_rgb(RgbParams rp, bool grad, cudaStream_t st) {
-    static int warps_resident = 0;   // per instantiation (T); GRAD variants share the register budget
+    static PerDevice resident;   // per instantiation (T); GRAD variants share the register budget
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    int warps_resident = resident.get(dev);
     if (!warps_resident) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgb_strip_kernel<T, true, false>, kRgbThreads, 0);
-        if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "rgb_strip_kernel occupancy query: %s", cudaGetErrorString(e));
-        warps_resident = sms * per_sm * (kRgbThreads / 32);
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgb_strip_kernel<T, true, false>, kRgbThreads, 0);
+        if (e != cudaSuccess || per_sm < 1) return fail(VLG_ERR_CUDA, "rgb_strip_kernel occupancy query: %s", cudaGetErrorString(e));
+        warps_resident = sm_count() * per_sm * (kRgbThreads / 32);
+        resident.set(dev, warps_resident);
     }
     int64_t warps = warps_resident < kRgbMaxWarps ? warps_resident : kRgbMaxWarps;
     const int64_t min_rows = 12;   // shorter runs are dominated by the 4 warm-up rows of a segment
@@ -569,52 +600,22 @@ static int launch_rgb(RgbParams rp, bool grad, cudaStream_t st) {
     return check_launch("rgb_strip_kernel");
 }
 
-// Persistent-warp launch of the layout strip kernel (fp32 layouts with K % 4 == 0: TMA-able rows).
-template <int K>
-static int launch_lay(LayParams lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
-    using WS = LayWarpSmem<float, K>;
-#ifdef VLG_LAY_ONE_CTA   // tuning experiment: pad shared memory so that a single CTA fits an SM
-    const size_t smem = 200 * 1024;
-#else
-    const size_t smem = sizeof(WS) * kLayWarps;
-#endif
-    static int warps_resident = 0;
-    if (!warps_resident) {
-        cudaError_t e = cudaFuncSetAttribute(lay_strip_kernel<float, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(lay_strip_kernel<float, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0, sms = 0, per_sm = 0;
-        if (e == cudaSuccess) e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lay_strip_kernel<float, K, true>, kLayThreads, smem);
-        if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "lay_strip_kernel setup: %s", cudaGetErrorString(e));
-        warps_resident = sms * per_sm * kLayWarps;
-    }
-    int64_t warps = warps_resident < kLayMaxWarps ? warps_resident : kLayMaxWarps;
-    const int64_t min_rows = 8;
-    if (warps * min_rows > lp.total_rows) warps = (lp.total_rows + min_rows - 1) / min_rows;
-    const int64_t blocks = (warps + kLayWarps - 1) / kLayWarps;
-    lp.chunk = (lp.total_rows + blocks * kLayWarps - 1) / (blocks * kLayWarps);
-    if (grad) lay_strip_kernel<float, K, true><<<(unsigned)blocks, kLayThreads, smem, st>>>(lp, map);
-    else lay_strip_kernel<float, K, false><<<(unsigned)blocks, kLayThreads, smem, st>>>(lp, map);
-    return check_launch("lay_strip_kernel");
-}
-
 // Persistent launch of the double-buffered layout tile kernel: one wave of resident CTAs.
 template <typename T, int K, bool PX8>
 static int launch_laytile(const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
     const size_t smem = sizeof(LayTileSmem<T, K>);
-    static int ctas_resident = 0;
+    static PerDevice resident, attr_g, attr_n;
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    if (int rc = ensure_smem(attr_g, lay_tile_kernel<T, K, true, PX8>, smem, "lay_tile")) return rc;
+    if (int rc = ensure_smem(attr_n, lay_tile_kernel<T, K, false, PX8>, smem, "lay_tile")) return rc;
+    int ctas_resident = resident.get(dev);
     if (!ctas_resident) {
-        cudaError_t e = cudaFuncSetAttribute(lay_tile_kernel<T, K, true, PX8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(lay_tile_kernel<T, K, false, PX8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0, sms = 0, per_sm = 0;
-        if (e == cudaSuccess) e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lay_tile_kernel<T, K, true, PX8>, kThreads, smem);
-        if (e != cudaSuccess || sms < 1 || per_sm < 1) return fail(VLG_ERR_CUDA, "lay_tile_kernel setup: %s", cudaGetErrorString(e));
-        ctas_resident = sms * per_sm;
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lay_tile_kernel<T, K, true, PX8>, kThreads, smem);
+        if (e != cudaSuccess || per_sm < 1) return fail(VLG_ERR_CUDA, "lay_tile_kernel setup: %s", cudaGetErrorString(e));
+        ctas_resident = sm_count() * per_sm;
+        resident.set(dev, ctas_resident);
     }
     const int64_t n_tiles = (int64_t)lp.N * lp.strips * lp.tiles_y;
     int64_t blocks = ctas_resident < kLayMaxWarps ? ctas_resident : kLayMaxWarps;
@@ -637,13 +638,6 @@ static int dispatch_laytile(const vlg_problem_t *prob, const LayParams &lp, cons
     VLG_FOR_EACH_K(X)
 #undef X
     return fail(VLG_ERR_UNSUPPORTED, "layout tile kernel: K / dtype not compiled in");
-}
-
-static int dispatch_lay(const vlg_problem_t *prob, const LayParams &lp, const CUtensorMap &map, bool grad, cudaStream_t st) {
-#define X(k) if constexpr ((k) % 4 == 0) { if (prob->K == k) return launch_lay<k>(lp, map, grad, st); }
-    VLG_FOR_EACH_K(X)
-#undef X
-    return fail(VLG_ERR_UNSUPPORTED, "layout strip kernel: K not compiled in");
 }
 
 // Side stream + fork/join events of the calling thread (created once per thread and device).  Used to run the
@@ -766,8 +760,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     if (warp && has_lay && prob->K % 4 == 0 && !(prob->flags & (VLG_FLAG_NO_TMA | VLG_FLAG_TILE_LAYOUT))) {
         CUtensorMap row_map;
         bool px8 = false;
-        const bool strips = (prob->flags & VLG_FLAG_STRIP_LAYOUT) != 0 && prob->dtype == VLG_F32;
-        if (strips ? make_layout_map(prob, src_layout, &row_map, kLBW, 1) : make_window_map(prob, src_layout, &row_map, kTSW, kTSH, &px8)) {
+        if (make_window_map(prob, src_layout, &row_map, kTSW, kTSH, &px8)) {
             LayParams lp{};
             lp.cc = pp.cc;
             lp.N = pp.N; lp.strips = pp.tiles_x; lp.tiles_y = pp.tiles_y;
@@ -779,7 +772,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.accum_dcoords = pp.accum_dcoords;
             lp.d_coords = need_grad ? d_coords : nullptr;
             lp.d_out_lay = need_grad ? (float *)d_out_lay : nullptr;
-            if (want_records && !strips) {
+            if (want_records) {
                 lp.rec_code = (uint32_t *)(ws + L.rec_code); lp.rec_frac = (float2 *)(ws + L.rec_frac); lp.pitch = (int)L.pitch;
                 records_done = true;
             }
@@ -787,7 +780,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.partials = (float *)(ws + L.partials_lay);
             lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
             lp.red = pp.red; lp.hdr = hdr;
-            rc = strips ? dispatch_lay(prob, lp, row_map, need_grad, st) : dispatch_laytile(prob, lp, row_map, px8, need_grad, st);
+            rc = dispatch_laytile(prob, lp, row_map, px8, need_grad, st);
             if (rc) return rc;
             lay_done = true;
         }
@@ -1057,8 +1050,8 @@ int vlg_scale_grads(void *g, int64_t n, int32_t dtype, const float *scale, void 
     if (!g || !scale || n < 0) return fail(VLG_ERR_ARG, "bad arguments to vlg_scale_grads");
     if (n == 0) return VLG_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == VLG_F32) scale_kernel<float><<<148 * 8, 256, 0, st>>>((float *)g, n, scale);
-    else if (dtype == VLG_BF16) scale_kernel<__nv_bfloat16><<<148 * 8, 256, 0, st>>>((__nv_bfloat16 *)g, n, scale);
+    if (dtype == VLG_F32) scale_kernel<float><<<sm_count() * 8, 256, 0, st>>>((float *)g, n, scale);
+    else if (dtype == VLG_BF16) scale_kernel<__nv_bfloat16><<<sm_count() * 8, 256, 0, st>>>((__nv_bfloat16 *)g, n, scale);
     else return fail(VLG_ERR_ARG, "bad dtype");
     return check_launch("scale_kernel");
 }

@@ -28,9 +28,9 @@ struct WsHeader {
     uint32_t n_rgb;         // per-warp partial rows written by rgb_strip_kernel (0: it did not run)
     double ce_denom;        // divisor of the weighted CE sum: sum_k w_k * hist_k (VLG_CE_NORM_TORCH with weights)
     uint32_t n_tile;        // partial rows written by the tile kernel (pass1_kernel), 0: it did not run
-    uint32_t n_lay;         // per-warp partial rows written by lay_strip_kernel
+    uint32_t n_lay;         // per-CTA partial rows written by lay_tile_kernel
     uint32_t pad[2];
-    unsigned long long prof[8];   // VLG_LAY_PROFILE builds: cycles per section of lay_strip_kernel, summed over warps
+    unsigned long long prof[8];   // spare (tuning builds: per-section cycle counters)
     unsigned long long hist[32];  // labels per class (only filled when class weights are given)
 };
 static_assert(sizeof(WsHeader) == 384, "header size");

@@ -1,6 +1,6 @@
 // vlg_laytile.cuh -- the layout half of pass 1 as a PERSISTENT, double-buffered tile kernel.
 //
-// Same arithmetic as vlg_lay.cuh (reference gongaa/video-layout-generation):
+// What it computes (reference gongaa/video-layout-generation):
 //   warp of the K-channel layout  (absent upstream) F.grid_sample(bilinear, align_corners=True) on
 //                                 the src/models/modules.py:69 grid, bit-exact FMA chain (App. A.6)
 //   argmax layouts                src/trainer.py:342,423,467 (first maximal index)
@@ -8,13 +8,13 @@
 //   TV on the flow                (absent upstream) stencils of src/loss.py:22,24
 // plus d(loss)/d(warped layout), the layout + TV part of d(loss)/d(coords) and pass 2's bookkeeping.
 //
-// Why a third organisation.  Measured on B200 (profiles/): a warp of this path runs at ~6 cycles per
+// Why this organisation.  Measured on B200 (profiles/): a warp of this path runs at ~6 cycles per
 // instruction whatever else the SM does (in-order issue, LDS / MUFU / integer chains), so throughput
-// is (resident warps) / (instructions per pixel).  The per-warp strip kernel (vlg_lay.cuh) pays ~250
-// instructions of ring bookkeeping per 32 pixels and its 16 KB ring per warp caps the SM at 12 warps;
-// the first tile kernel (vlg_pass1.cuh) amortised the bookkeeping over 256 pixels but exposed three
-// dependent global round trips per CTA.  This kernel keeps the tile (one TMA window per 32x8 pixels,
-// 4.8 KB per warp) and removes the exposed latency with a software pipeline over the CTA's tiles:
+// is (resident warps) / (instructions per pixel).  A per-warp strip kernel with a TMA row ring (round 1,
+// dropped) paid ~250 instructions of ring bookkeeping per 32 pixels and its 16 KB ring per warp capped the
+// SM at 12 warps; the first tile kernel (vlg_pass1.cuh) amortised the bookkeeping over 256 pixels but
+// exposed three dependent global round trips per CTA.  This kernel keeps the tile (one TMA window per
+// 32x8 pixels, 4.8 KB per warp) and removes the exposed latency with a software pipeline over the CTA's tiles:
 //   iteration i:  issue the TMA window of tile i+1 (origin from sums accumulated during iteration i-1)
 //                 issue the loads of tile i+3's coordinates / tile i+1's labels
 //                 wait for tile i's window, compute tile i
@@ -25,7 +25,6 @@
 #include <cuda.h>
 
 #include "vlg_device.cuh"
-#include "vlg_lay.cuh"     // bulk_store helpers
 #include "vlg_pass1.cuh"   // mbarrier / TMA helpers, source_xy, taps_from_xy
 
 namespace vlg {
@@ -39,6 +38,38 @@ template <> __device__ __forceinline__ float4 load4_smem<__nv_bfloat16>(const __
     const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
     return make_float4(a.x, a.y, b.x, b.y);
 }
+
+constexpr int kLayMaxWarps = 8192;    // partial-sum rows reserved in the workspace (one per CTA of the persistent grid)
+
+struct LayParams {
+    CoordCfg cc;
+    int N, strips;                 // strips = ceil(W / kTW)
+    int tiles_y;                   // ceil(H / kTH) (tile geometry of pass 2)
+    int64_t total_rows, chunk;
+    const void *src_layout;
+    const float *coords;
+    const int64_t *label;
+    int64_t ignore_index;
+    const float *class_weight;
+    int weighted_denom;
+    float w_ce_over_scale;
+    float c_tvh, c_tvw;
+    int do_tv;
+    int accum_dcoords;             // d_coords already holds the rgb part (the rgb strip kernel ran before): add to it
+    float *d_coords;               // nullable (validation)
+    float *d_out_lay;              // [P][K] fp32 staging, nullable
+    uint32_t *rec_code;            // [N][H][pitch] tap records for pass 2 (tap_cell_code), nullable
+    float2 *rec_frac;              // [N][H][pitch] fractional tap weights (ix - x0, iy - y0)
+    int pitch;
+    int64_t *out_argmax;           // nullable
+    float *partials;               // [n_ctas][4]: ce, tv_h, tv_w, -
+    float *tile_disp;              // [n_tiles] max NEAR displacement per 32x8 tile (zero-initialised, atomicMax)
+    int *far_list;
+    uint32_t *tile_flags;
+    int *flagged_list;
+    ReduceParams red;
+    WsHeader *hdr;
+};
 
 constexpr int kTSW = 40, kTSH = 12;   // staged window (pixels)
 constexpr int kFW = kTW + 2, kFH = kTH + 2;   // flow block with a halo of one pixel (TV stencil)

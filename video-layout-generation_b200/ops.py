@@ -41,7 +41,7 @@ class WarpLossConfig:
     use_tma: bool = True                  # stage source layout rows / windows with TMA tensor maps when possible
     tile_kernels: bool = False            # evaluate ALL of pass 1 in the first (non-persistent) 32x8 tile kernel
     layout_kernel: str = "tile2"          # layout half of pass 1: 'tile2' persistent double-buffered tile kernel (default),
-                                          # 'strip' per-warp TMA row ring, 'tile' first tile kernel
+                                          # 'tile' first tile kernel
     pass2_records: bool = True            # pass 2 gathers from the tap records pass 1 wrote (all staging by TMA);
                                           # False: it re-derives them from the coordinates (first pass-2 kernel)
     term_mask: int = 0                    # 0 = all terms
@@ -111,9 +111,9 @@ def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
         flags |= _cabi.FLAG_TILE_RGB | _cabi.FLAG_TILE_LAYOUT
     if not cfg.pass2_records:
         flags |= _cabi.FLAG_PASS2_COORDS
-    if cfg.layout_kernel not in ("tile2", "strip", "tile"):
-        raise VlgError(f"layout_kernel must be 'tile2', 'strip' or 'tile', not {cfg.layout_kernel!r}")
-    flags |= {"tile2": 0, "strip": _cabi.FLAG_STRIP_LAYOUT, "tile": _cabi.FLAG_TILE_LAYOUT}[cfg.layout_kernel]
+    if cfg.layout_kernel not in ("tile2", "tile"):
+        raise VlgError(f"layout_kernel must be 'tile2' or 'tile', not {cfg.layout_kernel!r}")
+    flags |= {"tile2": 0, "tile": _cabi.FLAG_TILE_LAYOUT}[cfg.layout_kernel]
     return Problem(N=N, H=H, W=W, K=K, dtype=_DTYPES[dtype], padding=_PADDING[cfg.padding_mode],
                    coord_mode=_cabi.COORD_GRID if cfg.coords_are_grid else _cabi.COORD_FLOW, flags=flags,
                    ignore_index=cfg.ignore_index, w_l1=cfg.w_l1, w_gd=cfg.w_gd, w_ssim=cfg.w_ssim,
