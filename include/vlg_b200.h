@@ -17,6 +17,10 @@
  *                            src/models/modules.py:69 grid + torch.argmax(seg, 1) src/trainer.py:342,467
  *   vlg_warp_loss_*       <- the fused op that replaces src/trainer.py:248-258 when the producer
  *                            emits flow instead of pixels
+ *   vlg_warp_loss_labels_fwd_bwd <- the same with the layout source as the class-id map the reference
+ *                            actually holds (one_hot(label): src/models/net_utils.py:14-24, src/trainer.py:461)
+ *   vlg_ingest            <- ToTensor src/data.py:33-35 + renormalisation src/trainer.py:193-195 + flip :200-206
+ *                            + seg casts src/folder.py:97-100 + one-hot, from the dataset's uint8 arrays
  *   vlg_reduce_partials   <- the scalar losses handed to Trainer.sync  src/trainer.py:381-386
  *
  * Memory layout: activations are NHWC ("channels_last" storage of an NCHW-logical tensor),
@@ -33,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VLG_VERSION 100 /* major*100 + minor */
+#define VLG_VERSION 200 /* major*100 + minor */
 
 /* activation dtype (coords, d_coords, loss outputs are always fp32; labels int64) */
 #define VLG_F32 0
@@ -94,6 +98,9 @@ extern "C" {
 #define VLG_LOSS_SLOTS 8
 
 typedef struct vlg_problem {
+    uint32_t struct_size; /* sizeof(vlg_problem_t) as the CALLER compiled it; checked by every entry point, so a
+                           * stale binding (older, shorter struct) is refused instead of read out of bounds    */
+    uint32_t abi_version; /* VLG_VERSION the caller was written against (major must match)               */
     int64_t N, H, W, K;   /* batch, output height/width (== source size), layout classes          */
     int32_t dtype;        /* VLG_F32 | VLG_BF16                                                    */
     int32_t padding;      /* VLG_PAD_*                                                             */
@@ -199,6 +206,31 @@ int vlg_warp_loss_fwd_bwd(const vlg_problem_t *prob, const void *src_rgb, const 
                           const float *coords, const void *tgt_rgb, const int64_t *tgt_label,
                           float *loss_out, float *d_coords, void *d_src_rgb, void *d_src_layout,
                           int64_t *out_argmax, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The fused op with a LABEL layout source: src_label [N,H,W] i64 stands for one_hot(src_label)
+ * (src/models/net_utils.py:14-24; the rollout feeds argmax maps back the same way, src/trainer.py:461,467).  Sources are
+ * data here, as in the reference: the gradient goes to the coordinates only (d_coords nullable = validation).
+ *   out_argmax == argmax_k warp(one_hot(src_label))_k bit for bit; losses / d_coords equal the dense path's on
+ *   one-hot inputs to fp32 rounding (same formulas, sums over the <= 4 non-zero channels instead of K).
+ * Workspace: vlg_workspace_bytes(prob, 0). */
+int vlg_warp_loss_labels_fwd_bwd(const vlg_problem_t *prob, const void *src_rgb, const int64_t *src_label,
+                                 const float *coords, const void *tgt_rgb, const int64_t *tgt_label, float *loss_out,
+                                 float *d_coords, int64_t *out_argmax, void *workspace, size_t workspace_bytes,
+                                 void *stream);
+
+/* Ingest of what the dataset holds (src/folder.py:85-104: uint8 RGB frames [N,H,W,3] from cv2, uint8 class maps
+ * [N,H,W]) in one pass per tensor, bit-identical to the reference's torch expressions:
+ *   out_frames [N,H,W,3] of the problem's dtype = ((u8 / 255) - mean[c]) / std[c]   ToTensor src/data.py:33-35, then
+ *              src/trainer.py:193-195; mean3 == NULL: u8 / 255 only.  mean3 / std3 are HOST pointers to 3 floats.
+ *   flip_w     torch.flip(frame, [3]) / torch.flip(seg, [2])                         src/trainer.py:200-206
+ *   out_label  [N,H,W] i64 = seg.long()                       src/folder.py:100      (nullable)
+ *   out_seg_f32 [N,H,W] f32 = seg.float()                     src/folder.py:97-99    (nullable)
+ *   out_onehot [N,H,W,K] of the problem's dtype               src/models/net_utils.py:14-24 (nullable)
+ * Either of (frames_u8, out_frames) / (seg_u8, outputs) may be NULL pairs.  `workspace` (nullable) receives
+ * VLG_STATUS_BAD_LABEL for class ids >= K when a one-hot layout is written. */
+int vlg_ingest(const vlg_problem_t *prob, const uint8_t *frames_u8, const float *mean3, const float *std3, int32_t flip_w,
+               void *out_frames, const uint8_t *seg_u8, int64_t *out_label, float *out_seg_f32, void *out_onehot,
+               void *workspace, void *stream);
 
 /* The reference's own loss call sites without a warp: `output` rgb [N,H,W,3] vs `target`,
  * `logits` [N,H,W,K] vs `tgt_label`.  Any of (out_rgb+tgt_rgb) / (logits+tgt_label) may be NULL

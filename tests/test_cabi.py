@@ -29,10 +29,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert set(declared) == set(_cabi.EXPORTS), (declared, _cabi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vlg_version() == 100
+    assert lib.vlg_version() == 200 == _cabi.ABI_VERSION
 
 
-def test_problem_struct_layout_matches_c():
+FIELDS = ["struct_size", "abi_version", "N", "H", "W", "K", "dtype", "padding", "coord_mode", "flags", "ignore_index", "w_l1", "w_gd",
+          "w_ssim", "w_ce", "w_tv", "term_mask", "ce_norm", "global_N", "ce_class_weight"]
+
+
+def _c_layout():
+    """sizeof(vlg_problem_t) and the offset of every field, from the header as gcc compiles it."""
     src = r'''
 #include <stdio.h>
 #include <stddef.h>
@@ -40,21 +45,53 @@ def test_problem_struct_layout_matches_c():
 int main(void){
   printf("%zu", sizeof(vlg_problem_t));
 #define O(f) printf(" %zu", offsetof(vlg_problem_t, f));
-  O(N) O(H) O(W) O(K) O(dtype) O(padding) O(coord_mode) O(flags) O(ignore_index)
-  O(w_l1) O(w_gd) O(w_ssim) O(w_ce) O(w_tv) O(term_mask) O(ce_norm) O(global_N) O(ce_class_weight)
+  FIELDS
   return 0; }
-'''
+'''.replace("FIELDS", " ".join(f"O({f})" for f in FIELDS))
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "t")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
-        vals = [int(v) for v in subprocess.check_output([exe]).split()]
+        return [int(v) for v in subprocess.check_output([exe]).split()]
+
+
+def test_problem_struct_layout_matches_c():
+    vals = _c_layout()
     P = _cabi.Problem
-    names = ["N", "H", "W", "K", "dtype", "padding", "coord_mode", "flags", "ignore_index", "w_l1", "w_gd",
-             "w_ssim", "w_ce", "w_tv", "term_mask", "ce_norm", "global_N", "ce_class_weight"]
+    assert [n for n, _ in P._fields_] == FIELDS
     assert vals[0] == C.sizeof(P)
-    assert vals[1:] == [getattr(P, n).offset for n in names]
+    assert vals[1:] == [getattr(P, n).offset for n in FIELDS]
+    assert P().struct_size == vals[0] and P().abi_version == _cabi.ABI_VERSION
+
+
+def test_integration_doc_binding_matches_c():
+    """INTEGRATION.md shows a maintainer the ctypes mirror of vlg_problem_t: the DOCUMENT is what gets copied, so
+    the snippet itself is executed here and its layout compared with the header (round 1 shipped a stale one)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class Problem\(C\.Structure\):.*?\n(?=\S)", text, flags=re.S)
+    assert m, "INTEGRATION.md no longer contains the Problem mirror"
+    ns = {"C": C}
+    exec(m.group(0), ns)
+    D = ns["Problem"]
+    vals = _c_layout()
+    assert [n for n, _ in D._fields_] == FIELDS
+    assert C.sizeof(D) == vals[0]
+    assert [getattr(D, n).offset for n in FIELDS] == vals[1:]
+
+
+def test_stale_descriptor_is_refused():
+    """A caller compiled against an older, shorter vlg_problem_t (or one that never set struct_size) is told so
+    instead of having the library read past its buffer."""
+    lib = _cabi.load()
+    ok = _cabi.Problem(N=2, H=16, W=16, K=20, padding=1)
+    assert lib.vlg_workspace_bytes(C.byref(ok), 0) > 0
+    stale = _cabi.Problem(N=2, H=16, W=16, K=20, padding=1, struct_size=96)
+    assert lib.vlg_workspace_bytes(C.byref(stale), 0) == 0
+    assert b"struct_size" in lib.vlg_last_error()
+    old = _cabi.Problem(N=2, H=16, W=16, K=20, padding=1, abi_version=100)
+    assert lib.vlg_workspace_bytes(C.byref(old), 0) == 0
+    assert b"abi_version" in lib.vlg_last_error()
 
 
 def test_header_constants_match_binding():
@@ -97,6 +134,20 @@ def test_no_cpu_fallback():
         vlg_b200.L1Loss()(x, x)
     with pytest.raises(vlg_b200.VlgError):
         vlg_b200.warp(x, None, torch.zeros(1, 8, 8, 2))
+    with pytest.raises(vlg_b200.VlgError):
+        vlg_b200.ingest(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
+    with pytest.raises(vlg_b200.VlgError):
+        vlg_b200.warp_loss_labels(x, torch.zeros(1, 8, 8, dtype=torch.int64), torch.zeros(1, 8, 8, 2), x, torch.zeros(1, 8, 8, dtype=torch.int64))
+
+
+def test_build_is_atomic_and_locked():
+    """Every rank of a torchrun launch imports the package at once: the build must happen under a lock, into a
+    temporary file that is moved into place (no rank may dlopen a half-written library)."""
+    import inspect
+    from vlg_b200 import _build
+    src = inspect.getsource(_build.build_library)
+    assert "flock" in src and "os.replace" in src
+    assert not _build.is_stale(), "the in-tree library is older than its sources"
 
 
 def test_product_never_imports_oracle():

@@ -8,7 +8,7 @@ from . import _build, _cabi  # noqa: F401
 from ._cabi import VlgError, launch_count  # noqa: F401
 from .losses import (CombinedLoss, CrossEntropyLoss, GradientLoss, L1Loss, PixelLosses,  # noqa: F401
                      SsimLoss, WarpLoss)
-from .ops import (CITYSCAPES_PALETTE, WarpLossConfig, colorize, empty_nhwc, one_hot_layout, pixel_losses, prepare_frames, rollout,  # noqa: F401
-                  to_nhwc, warp, warp_labels, warp_loss)
+from .ops import (CITYSCAPES_PALETTE, WarpLossConfig, colorize, empty_nhwc, ingest, one_hot_layout, pixel_losses, prepare_frames,  # noqa: F401
+                  rollout, to_nhwc, warp, warp_labels, warp_loss, warp_loss_labels)
 
-__version__ = "1.0"
+__version__ = "2.0"

@@ -37,13 +37,32 @@ def is_stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into one shared library next to the package."""
+    """Compile every CUDA source into one shared library next to the package.
+
+    Safe under `torchrun --nproc-per-node N` (every rank imports the package at once): the compile runs under an
+    exclusive file lock, writes to a temporary file and is moved into place atomically, so no rank can dlopen a
+    half-written library; ranks that waited for the lock find a fresh library and skip the compile."""
+    import fcntl
+    import tempfile
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():      # another process built it while we waited
+                return LIB_PATH
+            fd, tmp = tempfile.mkstemp(prefix=".libvlg_b200.", suffix=".so.tmp", dir=PKG_DIR)
+            os.close(fd)
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.chmod(tmp, 0o755)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH

@@ -20,9 +20,11 @@ CE_NORM_TORCH, CE_NORM_COUNT = 0, 1
 NEAR_RADIUS = 3
 LOSS_L1, LOSS_GD, LOSS_SSIM, LOSS_CE, LOSS_TV, LOSS_TOTAL, LOSS_NVALID, LOSS_MAXDISP, LOSS_SLOTS = range(9)
 
+ABI_VERSION = 200
+
 EXPORTS = [
     "vlg_version", "vlg_last_error", "vlg_workspace_bytes", "vlg_warp_fwd", "vlg_warp_fwd_labels", "vlg_colorize", "vlg_one_hot",
-    "vlg_frame_affine",
+    "vlg_frame_affine", "vlg_ingest", "vlg_warp_loss_labels_fwd_bwd",
     "vlg_warp_loss_bwd_out", "vlg_warp_loss_pass1",
     "vlg_warp_bwd_src", "vlg_reduce_partials", "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd",
     "vlg_scale_grads", "vlg_read_status", "vlg_launch_count",
@@ -30,8 +32,10 @@ EXPORTS = [
 
 
 class Problem(C.Structure):
-    """Mirror of vlg_problem_t (include/vlg_b200.h)."""
+    """Mirror of vlg_problem_t (include/vlg_b200.h).  `struct_size` / `abi_version` are filled in by the
+    constructor; the library refuses a descriptor whose size differs from its own (stale binding)."""
     _fields_ = [
+        ("struct_size", C.c_uint32), ("abi_version", C.c_uint32),
         ("N", C.c_int64), ("H", C.c_int64), ("W", C.c_int64), ("K", C.c_int64),
         ("dtype", C.c_int32), ("padding", C.c_int32), ("coord_mode", C.c_int32), ("flags", C.c_uint32),
         ("ignore_index", C.c_int64),
@@ -39,6 +43,14 @@ class Problem(C.Structure):
         ("term_mask", C.c_uint32), ("ce_norm", C.c_uint32),
         ("global_N", C.c_int64), ("ce_class_weight", C.c_void_p),
     ]
+
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        if "struct_size" not in kw:
+            self.struct_size = C.sizeof(Problem)
+        if "abi_version" not in kw:
+            self.abi_version = ABI_VERSION
 
 
 class VlgError(RuntimeError):
@@ -62,11 +74,17 @@ def load(build_if_missing: bool = True):
     if override:
         path, build_if_missing = override, False
     if build_if_missing and _build.is_stale():
+        # A library older than its sources is never used silently: rebuild (atomically, under a file lock) or fail.
+        # On a box without nvcc a library that is present is accepted as shipped (the GPU box receives the built .so).
         try:
-            _build.build_library()
-        except Exception as exc:  # stale-but-present library is still usable; missing is fatal
-            if not os.path.exists(path):
-                raise VlgError(f"libvlg_b200.so is missing and could not be built: {exc}") from exc
+            have_nvcc = bool(_build._nvcc())
+        except RuntimeError:
+            have_nvcc = False
+        if have_nvcc or not os.path.exists(path):
+            try:
+                _build.build_library()
+            except Exception as exc:
+                raise VlgError(f"libvlg_b200.so is stale or missing and could not be rebuilt: {exc}") from exc
     if not os.path.exists(path):
         raise VlgError("libvlg_b200.so is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = C.CDLL(path)
@@ -85,6 +103,10 @@ def load(build_if_missing: bool = True):
     lib.vlg_one_hot.restype = C.c_int
     lib.vlg_frame_affine.argtypes = [P, f32p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_int32, vp, i64p, i64p, vp]
     lib.vlg_frame_affine.restype = C.c_int
+    lib.vlg_ingest.argtypes = [P, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, vp, vp, i64p, f32p, vp, vp, vp]
+    lib.vlg_ingest.restype = C.c_int
+    lib.vlg_warp_loss_labels_fwd_bwd.argtypes = [P, vp, i64p, f32p, vp, i64p, f32p, f32p, i64p, vp, C.c_size_t, vp]
+    lib.vlg_warp_loss_labels_fwd_bwd.restype = C.c_int
     lib.vlg_warp_loss_bwd_out.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, i64p, C.c_int, vp, C.c_size_t, vp]
     lib.vlg_warp_loss_pass1.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, f32p, i64p, C.c_int, vp, C.c_size_t, vp]
     lib.vlg_warp_loss_pass1.restype = C.c_int

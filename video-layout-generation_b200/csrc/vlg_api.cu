@@ -12,6 +12,8 @@
 #include "vlg_rgb.cuh"
 #include "vlg_laytile.cuh"
 #include "vlg_frames.cuh"
+#include "vlg_ingest.cuh"
+#include "vlg_labels.cuh"
 
 using namespace vlg;
 
@@ -94,6 +96,11 @@ static bool k_supported(int64_t K) {
 
 static int check_problem(const vlg_problem_t *p) {
     if (!p) return fail(VLG_ERR_ARG, "problem is NULL");
+    if (p->struct_size != sizeof(vlg_problem_t))
+        return fail(VLG_ERR_ARG, "vlg_problem_t.struct_size is %u, this library was built with %zu: stale binding of include/vlg_b200.h?",
+                    p->struct_size, sizeof(vlg_problem_t));
+    if (p->abi_version / 100 != VLG_VERSION / 100)
+        return fail(VLG_ERR_ARG, "vlg_problem_t.abi_version %u does not match the library's %d (major versions differ)", p->abi_version, VLG_VERSION);
     if (p->N < 1 || p->H < 2 || p->W < 2) return fail(VLG_ERR_ARG, "need N>=1, H>=2, W>=2 (got %lld,%lld,%lld)", (long long)p->N, (long long)p->H, (long long)p->W);
     if (p->N * p->H * p->W >= (1ll << 31)) return fail(VLG_ERR_UNSUPPORTED, "N*H*W must be < 2^31");
     if (p->N > 65535 || (p->H + 7) / 8 > 65535) return fail(VLG_ERR_UNSUPPORTED, "N and H/8 must fit a CUDA grid dimension (65535)");
@@ -800,6 +807,82 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     return rc;
 }
 
+// Pass 1 with a LABEL layout source: memset(header) -> (count_valid on the side stream, next to) rgb_strip_kernel ->
+// join -> lab_pix_kernel (layout terms from four label taps, TV, sum of d_coords, final reduction).
+static int run_pass1_labels(const vlg_problem_t *prob, const void *src_rgb, const int64_t *src_label, const float *coords,
+                            const void *tgt_rgb, const int64_t *tgt_label, float *d_coords, int64_t *out_argmax, float *loss_out,
+                            void *workspace, const WsLayout &L, cudaStream_t st) {
+    char *ws = (char *)workspace;
+    WsHeader *hdr = (WsHeader *)(ws + L.header);
+    const int64_t P = prob->N * prob->H * prob->W;
+    const bool has_lay = src_label && tgt_label, has_rgb = src_rgb && tgt_rgb;
+    if (!has_lay) return fail(VLG_ERR_UNSUPPORTED, "the label-source op needs src_label / tgt_label (use vlg_pixel_loss_* for rgb-only criteria)");
+    cudaError_t e = cudaMemsetAsync(hdr, 0, L.partials - L.header, st);
+    if (e != cudaSuccess) return fail(VLG_ERR_CUDA, "memset header: %s", cudaGetErrorString(e));
+    const bool need_grad = d_coords != nullptr;
+    bool join_count = false;
+    SideLane *lane = nullptr;
+    if (has_lay) {
+        cudaStream_t cst = st;
+        if (has_rgb && (lane = side_lane()) != nullptr && cudaEventRecord(lane->fork, st) == cudaSuccess &&
+            cudaStreamWaitEvent(lane->s, lane->fork, 0) == cudaSuccess) {
+            cst = lane->s;
+            join_count = true;
+        }
+        const int blocks = (int)((P + 256 * 16 - 1) / (256 * 16));
+        count_valid_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, cst>>>(tgt_label, P, prob->ignore_index, (int)prob->K, prob->ce_class_weight, hdr);
+        int rc = check_launch("count_valid_kernel");
+        if (join_count && cudaEventRecord(lane->join, lane->s) != cudaSuccess) return fail(VLG_ERR_CUDA, "side stream join record failed");
+        if (rc) return rc;
+    }
+    const double Ng = (double)(prob->global_N ? prob->global_N : prob->N);
+    const double H = (double)prob->H, W = (double)prob->W;
+    uint32_t terms = prob->term_mask ? prob->term_mask : VLG_TERM_ALL;
+    if (!(prob->H > 2 && prob->W > 2)) terms &= ~VLG_TERM_SSIM;
+    const CoordCfg cc = make_cc(prob);
+    if (has_rgb) {
+        RgbParams rp{};
+        rp.cc = cc;
+        rp.N = (int)prob->N;
+        rp.strips = (int)((prob->W + kRS - 1) / kRS);
+        rp.total_rows = prob->N * rp.strips * prob->H;
+        rp.src_rgb = src_rgb; rp.tgt_rgb = tgt_rgb; rp.coords = coords;
+        rp.terms = terms;
+        rp.c_l1 = (terms & VLG_TERM_L1) ? (float)(prob->w_l1 / (Ng * 3 * H * W)) : 0.f;
+        rp.c_gd = (terms & VLG_TERM_GD) ? (float)(prob->w_gd / (Ng * 3 * H * W)) : 0.f;
+        rp.c_ssim = ((terms & VLG_TERM_SSIM) && prob->H > 2 && prob->W > 2) ? (float)(prob->w_ssim / (2.0 * Ng * (H - 2) * (W - 2))) : 0.f;
+        rp.d_coords = need_grad ? d_coords : nullptr;
+        rp.d_out_rgb = nullptr;            // sources are data: no pass 2, no staging
+        rp.pitch = (int)L.pitch;
+        rp.partials = (float *)(ws + L.partials_rgb);
+        rp.hdr = hdr;
+        int rc0 = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
+        if (rc0) return rc0;
+    }
+    if (join_count && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return fail(VLG_ERR_CUDA, "side stream join failed");
+    LabParams lp{};
+    lp.cc = cc; lp.K = (int)prob->K; lp.P = P; lp.HW = prob->H * prob->W;
+    lp.src_label = src_label; lp.coords = (const float2 *)coords; lp.tgt_label = tgt_label; lp.ignore_index = prob->ignore_index;
+    lp.class_weight = prob->ce_class_weight;
+    lp.weighted_denom = prob->ce_class_weight != nullptr && prob->ce_norm == VLG_CE_NORM_TORCH;
+    lp.w_ce_over_scale = (float)(prob->w_ce * (double)prob->N / Ng);
+    lp.do_tv = prob->coord_mode == VLG_COORD_FLOW && (terms & VLG_TERM_TV);
+    lp.c_tvh = prob->H > 1 ? (float)(prob->w_tv / (Ng * (H - 1) * W * 2)) : 0.f;
+    lp.c_tvw = prob->W > 1 ? (float)(prob->w_tv / (Ng * H * (W - 1) * 2)) : 0.f;
+    lp.accum_dcoords = has_rgb ? 1 : 0;
+    lp.d_coords = d_coords; lp.out_argmax = out_argmax;
+    lp.partials = (float *)(ws + L.partials_lay);
+    lp.red = make_reduce_params(prob, L, ws, loss_out);
+    lp.hdr = hdr;
+    int64_t blocks = (int64_t)sm_count() * 8;
+    const int64_t max_blocks = (P + kLabThreads - 1) / kLabThreads;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks > kLayMaxWarps) blocks = kLayMaxWarps;
+    if (need_grad) lab_pix_kernel<true><<<(unsigned)blocks, kLabThreads, 0, st>>>(lp);
+    else lab_pix_kernel<false><<<(unsigned)blocks, kLabThreads, 0, st>>>(lp);
+    return check_launch("lab_pix_kernel");
+}
+
 template <typename T, int K>
 static int launch_colorize(int64_t P, const void *layout, const int64_t *label, const uint8_t *lut, void *out_rgb,
                            int64_t *out_label, cudaStream_t st) {
@@ -996,6 +1079,73 @@ int vlg_warp_loss_fwd_bwd(const vlg_problem_t *prob, const void *src_rgb, const 
                              loss_out, workspace, workspace_bytes, stream);
     if (rc) return rc;
     if (with_src) rc = vlg_warp_bwd_src(prob, coords, d_src_rgb, d_src_layout, workspace, workspace_bytes, stream);
+    return rc;
+}
+
+int vlg_warp_loss_labels_fwd_bwd(const vlg_problem_t *prob, const void *src_rgb, const int64_t *src_label, const float *coords,
+                                 const void *tgt_rgb, const int64_t *tgt_label, float *loss_out, float *d_coords,
+                                 int64_t *out_argmax, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if (!coords) return fail(VLG_ERR_ARG, "coords is NULL");
+    if ((src_rgb == nullptr) != (tgt_rgb == nullptr)) return fail(VLG_ERR_ARG, "src_rgb and tgt_rgb go together");
+    if ((src_label == nullptr) != (tgt_label == nullptr)) return fail(VLG_ERR_ARG, "src_label and tgt_label go together");
+    if (!src_rgb && !src_label) return fail(VLG_ERR_ARG, "nothing to evaluate");
+    const WsLayout L = ws_layout(prob, 0);
+    if (!workspace || workspace_bytes < L.total) return fail(VLG_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
+    return run_pass1_labels(prob, src_rgb, src_label, coords, tgt_rgb, tgt_label, d_coords, out_argmax, loss_out, workspace, L,
+                            (cudaStream_t)stream);
+}
+
+int vlg_ingest(const vlg_problem_t *prob, const uint8_t *frames_u8, const float *mean3, const float *std3, int32_t flip_w,
+               void *out_frames, const uint8_t *seg_u8, int64_t *out_label, float *out_seg_f32, void *out_onehot,
+               void *workspace, void *stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if ((frames_u8 == nullptr) != (out_frames == nullptr)) return fail(VLG_ERR_ARG, "frames_u8 and out_frames go together");
+    if ((mean3 == nullptr) != (std3 == nullptr)) return fail(VLG_ERR_ARG, "mean3 and std3 go together");
+    if (seg_u8 && !out_label && !out_seg_f32 && !out_onehot) return fail(VLG_ERR_ARG, "seg_u8 given but no output for it");
+    if (!seg_u8 && (out_label || out_seg_f32 || out_onehot)) return fail(VLG_ERR_ARG, "segmentation outputs need seg_u8");
+    if (!frames_u8 && !seg_u8) return fail(VLG_ERR_ARG, "nothing to ingest");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t P = prob->N * prob->H * prob->W;
+    const int W = (int)prob->W, flip = flip_w ? 1 : 0;
+    if (frames_u8) {
+        IngestNorm nm{};
+        nm.normalize = mean3 != nullptr;
+        for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3 ? mean3[c] : 0.f; nm.std[c] = std3 ? std3[c] : 1.f; }
+        const bool vec = W % 4 == 0 && ((uintptr_t)frames_u8) % 4 == 0 && ((uintptr_t)out_frames) % 16 == 0;
+        if (vec) {
+            const int64_t groups = P / 4;
+            const unsigned blocks = (unsigned)((groups + 255) / 256);
+            if (prob->dtype == VLG_F32) ingest_frames_vec4_kernel<float><<<blocks, 256, 0, st>>>(nm, groups, W, flip, frames_u8, (float *)out_frames);
+            else ingest_frames_vec4_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(nm, groups, W, flip, frames_u8, (__nv_bfloat16 *)out_frames);
+        } else {
+            const unsigned blocks = (unsigned)((P + 255) / 256);
+            if (prob->dtype == VLG_F32) ingest_frames_px_kernel<float><<<blocks, 256, 0, st>>>(nm, P, W, flip, frames_u8, (float *)out_frames);
+            else ingest_frames_px_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(nm, P, W, flip, frames_u8, (__nv_bfloat16 *)out_frames);
+        }
+        rc = check_launch("ingest_frames_kernel");
+        if (rc) return rc;
+    }
+    if (seg_u8) {
+#define X(k)                                                                                                                       \
+        if (prob->K == k) {                                                                                                        \
+            if (prob->dtype == VLG_F32) {                                                                                          \
+                const int64_t n = P * ((out_onehot && (k % 4) == 0) ? k / 4 : 1);                                                  \
+                ingest_seg_kernel<float, k><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, W, flip, seg_u8, out_label, out_seg_f32, \
+                                                                                         (float *)out_onehot, (WsHeader *)workspace); \
+            } else {                                                                                                               \
+                const int64_t n = P * ((out_onehot && (k % 8) == 0) ? k / 8 : 1);                                                  \
+                ingest_seg_kernel<__nv_bfloat16, k><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(                                  \
+                    P, W, flip, seg_u8, out_label, out_seg_f32, (__nv_bfloat16 *)out_onehot, (WsHeader *)workspace);               \
+            }                                                                                                                      \
+            return check_launch("ingest_seg_kernel");                                                                             \
+        }
+        VLG_FOR_EACH_K(X)
+#undef X
+        return fail(VLG_ERR_UNSUPPORTED, "K not compiled in");
+    }
     return rc;
 }
 

@@ -118,16 +118,19 @@ class PixelLosses(nn.Module):
 
 
 class WarpLoss(nn.Module):
-    """Fused flow-guided warp + losses.  forward(src_rgb, src_layout, flow, tgt_rgb, tgt_label)."""
+    """Fused flow-guided warp + losses.  forward(src_rgb, src_layout, flow, tgt_rgb, tgt_label).
+    `src_layout` is a [N,K,H,W] layout (one-hot or soft; differentiable) or the int64 [N,H,W] class-id map it
+    is the one-hot of (the reference's data, src/models/net_utils.py:14-24; label sources are not differentiable).
+    `debug=True` reads the device status word after every call (synchronises) and raises on out-of-range labels."""
 
     def __init__(self, weights=(40.0, 20.0, 10.0, 0.0), padding_mode="border", coords_are_grid=False,
-                 ignore_index=-100, global_batch=0, assume_near=False, want_argmax=False):
+                 ignore_index=-100, global_batch=0, assume_near=False, want_argmax=False, debug=False):
         super().__init__()
         w_l1, w_style, w_ce, w_tv = weights
         self.cfg = WarpLossConfig(w_l1=w_l1, w_gd=w_style, w_ssim=w_style, w_ce=w_ce, w_tv=w_tv,
                                   padding_mode=padding_mode, coords_are_grid=coords_are_grid,
                                   ignore_index=ignore_index, global_batch=global_batch,
-                                  assume_near=assume_near, want_argmax=want_argmax)
+                                  assume_near=assume_near, want_argmax=want_argmax, debug=debug)
         self.last_terms = None
         self.last_argmax = None
 

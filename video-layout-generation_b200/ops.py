@@ -48,12 +48,33 @@ class WarpLossConfig:
     class_weight: Optional[torch.Tensor] = None   # per-class CE weights (K floats on the device)
     ce_norm: str = "torch"                # 'torch' (weighted mean) | 'count' (sum / n_known, src/models/simple.py:56-59)
     want_argmax: bool = False
+    debug: bool = False                   # read the device status word after the call (synchronises) and raise on labels
+                                          # outside [0,K) (nn.CrossEntropyLoss device-asserts there) / far taps under assume_near
 
 
 def _require_cuda(*tensors):
+    """All tensors on ONE CUDA device (no CPU fallback); returns that device."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise VlgError("video-layout-generation_b200 runs on CUDA tensors only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise VlgError(f"all tensors must live on one device (got {dev} and {t.device})")
+    return dev
+
+
+def _expect(t: Optional[torch.Tensor], shape, what: str, dtype=None):
+    """torch would raise a shape error where raw pointers would read out of bounds: check before data_ptr()."""
+    if t is None:
+        return
+    if tuple(t.shape) != tuple(shape):
+        raise VlgError(f"{what} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    if dtype is not None and t.dtype != dtype:
+        raise VlgError(f"{what} must be {dtype}, got {t.dtype}")
 
 
 def _nhwc_strides(shape):
@@ -122,12 +143,37 @@ def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
                    global_N=cfg.global_batch, ce_class_weight=_class_weight_ptr(cfg, K))
 
 
-def _workspace(prob: Problem, with_src: bool, device) -> torch.Tensor:
+# Workspaces are scratch for ONE call (both passes are launched inside it; the gradients live in their own
+# tensors), so successive calls on the same stream reuse one buffer: stream order serialises them.  Keyed by
+# (device, stream); grown on demand; a handful of streams at most.
+_WS_CACHE: dict = {}
+
+
+def _workspace(prob: Problem, with_src: bool, device, cached: bool = True) -> torch.Tensor:
     lib = _cabi.load()
     n = lib.vlg_workspace_bytes(C.byref(prob), int(with_src))
     if n == 0:
         raise VlgError(lib.vlg_last_error().decode())
-    return torch.empty(n, dtype=torch.uint8, device=device)
+    if not cached:
+        return torch.empty(n, dtype=torch.uint8, device=device)
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < n:
+        if len(_WS_CACHE) >= 8:
+            _WS_CACHE.clear()
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def _check_status(ws: torch.Tensor, cfg: "WarpLossConfig"):
+    """debug mode: the status word is sticky until the next pass-1 launch on this workspace."""
+    st = read_status(ws)
+    if st & _cabi.STATUS_BAD_LABEL:
+        raise VlgError("a target label lies outside [0, K) and is not ignore_index (nn.CrossEntropyLoss asserts on the device here)")
+    if st & _cabi.STATUS_FAR_TAPS:
+        raise VlgError(f"assume_near=True but a sampling position lies >= {_cabi.NEAR_RADIUS} px from its pixel: "
+                       "source-gradient contributions were dropped")
 
 
 # --------------------------------------------------------------------------- forward-only warp
@@ -138,24 +184,28 @@ def warp(src_rgb: Optional[torch.Tensor], src_layout: Optional[torch.Tensor], co
     """Validation / rollout warp (src/trainer.py:329-342,460-469).  Returns
     (warped_rgb | None, warped_layout | None, argmax | None[, x0y0 int32])."""
     lib = _cabi.load()
-    _require_cuda(src_rgb, src_layout, coords)
+    dev = _require_cuda(src_rgb, src_layout, coords)
     ref = src_rgb if src_rgb is not None else src_layout
     if ref is None:
         raise VlgError("warp needs at least one source tensor")
+    if ref.dim() != 4:
+        raise VlgError(f"sources must be NCHW-logical 4-d tensors, got shape {tuple(ref.shape)}")
     N, _, H, W = ref.shape
     K = src_layout.shape[1] if src_layout is not None else 20
+    _expect(src_rgb, (N, 3, H, W), "src_rgb")
+    _expect(src_layout, (N, K, H, W), "src_layout", ref.dtype)
     cfg = WarpLossConfig(padding_mode=padding_mode, coords_are_grid=coords_are_grid)
     prob = _problem(N, H, W, K, ref.dtype, cfg)
     coords = _coords(coords, N, H, W)
-    dev = ref.device
     a = to_nhwc(src_rgb) if src_rgb is not None else None
     b = to_nhwc(src_layout) if src_layout is not None else None
     out_rgb = empty_nhwc((N, 3, H, W), ref.dtype, dev) if a is not None else None
     out_lay = empty_nhwc((N, K, H, W), ref.dtype, dev) if (b is not None and want_layout) else None
     out_arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if (b is not None and want_argmax) else None
     dbg = torch.empty((N, H, W, 2), dtype=torch.int32, device=dev) if debug_indices else None
-    check(lib.vlg_warp_fwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(coords), _ptr(out_rgb), _ptr(out_lay),
-                           _ptr(out_arg), _ptr(dbg), _stream()))
+    with torch.cuda.device(dev):
+        check(lib.vlg_warp_fwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(coords), _ptr(out_rgb), _ptr(out_lay),
+                               _ptr(out_arg), _ptr(dbg), _stream()))
     res = (out_rgb, out_lay, out_arg)
     return res + (dbg,) if debug_indices else res
 
@@ -167,10 +217,11 @@ def warp_labels(src_rgb: Optional[torch.Tensor], src_label: torch.Tensor, coords
     warped_label int64 [N,H,W]) where warped_label == argmax(warp(one_hot(src_label))) bit for bit,
     at 8 B/px of layout traffic instead of 80."""
     lib = _cabi.load()
-    _require_cuda(src_rgb, src_label, coords)
+    dev = _require_cuda(src_rgb, src_label, coords)
     if src_label.dtype != torch.int64 or src_label.dim() != 3:
         raise VlgError("src_label must be int64 [N,H,W]")
     N, H, W = src_label.shape
+    _expect(src_rgb, (N, 3, H, W), "src_rgb")
     dt = src_rgb.dtype if src_rgb is not None else torch.float32
     prob = _problem(N, H, W, 20, dt, WarpLossConfig(padding_mode=padding_mode, coords_are_grid=coords_are_grid))
     coords = _coords(coords, N, H, W)
@@ -178,7 +229,8 @@ def warp_labels(src_rgb: Optional[torch.Tensor], src_label: torch.Tensor, coords
     lab = src_label.contiguous()
     out_rgb = empty_nhwc((N, 3, H, W), dt, lab.device) if a is not None else None
     out_lab = torch.empty_like(lab)
-    check(lib.vlg_warp_fwd_labels(C.byref(prob), _ptr(a), _ptr(lab), _ptr(coords), _ptr(out_rgb), _ptr(out_lab), _stream()))
+    with torch.cuda.device(dev):
+        check(lib.vlg_warp_fwd_labels(C.byref(prob), _ptr(a), _ptr(lab), _ptr(coords), _ptr(out_rgb), _ptr(out_lab), _stream()))
     return out_rgb, out_lab
 
 
@@ -212,7 +264,8 @@ def colorize(seg: torch.Tensor, n_classes: int = 20, argmax: bool = False, palet
         lay, lab, dt = None, seg.contiguous(), dtype
     prob = _problem(N, H, W, n_classes, dt, WarpLossConfig())
     out = empty_nhwc((N, 3, H, W), dt, seg.device)
-    check(lib.vlg_colorize(C.byref(prob), _ptr(lay), _ptr(lab), _ptr(lut), _ptr(out), None, _stream()))
+    with torch.cuda.device(seg.device):
+        check(lib.vlg_colorize(C.byref(prob), _ptr(lay), _ptr(lab), _ptr(lut), _ptr(out), None, _stream()))
     return out
 
 
@@ -236,7 +289,8 @@ def one_hot_layout(seg: torch.Tensor, n_classes: int = 20, dtype: torch.dtype = 
     out = empty_nhwc((N, n_classes, H, W), dtype, seg.device)
     lib = _cabi.load()
     li, lf = (_ptr(seg), None) if seg.dtype == torch.int64 else (None, _ptr(seg))
-    check(lib.vlg_one_hot(C.byref(prob), li, lf, _ptr(out), None, _stream()))
+    with torch.cuda.device(seg.device):
+        check(lib.vlg_one_hot(C.byref(prob), li, lf, _ptr(out), None, _stream()))
     return out
 
 
@@ -272,9 +326,54 @@ def prepare_frames(frames: torch.Tensor, mean=IMG_MEAN, std=IMG_STD, *, flip: bo
             raise VlgError(f"labels must be int64 [N,H,W]={N, H, W}")
         labels = labels.contiguous()
         lab_out = torch.empty_like(labels)
-    check(_cabi.load().vlg_frame_affine(C.byref(prob), _ptr(frames), int(not nhwc), a3, b3, int(denormalize), int(flip),
-                                        _ptr(out), _ptr(labels), _ptr(lab_out), _stream()))
+    with torch.cuda.device(frames.device):
+        check(_cabi.load().vlg_frame_affine(C.byref(prob), _ptr(frames), int(not nhwc), a3, b3, int(denormalize), int(flip),
+                                            _ptr(out), _ptr(labels), _ptr(lab_out), _stream()))
     return out if labels is None else (out, lab_out)
+
+
+@torch.no_grad()
+def ingest(frames_u8: Optional[torch.Tensor] = None, seg_u8: Optional[torch.Tensor] = None, *, mean=IMG_MEAN, std=IMG_STD,
+           flip: bool = False, n_classes: int = 20, dtype: torch.dtype = torch.float32, want_label: bool = True,
+           want_seg_float: bool = False, want_one_hot: bool = False):
+    """What the dataset holds -> what the path consumes, one pass per tensor, bit-identical to the reference's
+    torch expressions (so a data pipeline uploads 3 + 1 bytes per pixel instead of 12 + 4 / 8).
+
+    frames_u8 uint8 [N,H,W,3] (cv2 / dataset layout, src/folder.py:122-127): `ToTensor()` (src/data.py:33-35, u8 / 255)
+              then `(frame - img_mean_arr) / img_std_arr` (src/trainer.py:193-195; mean=None: ToTensor only), optional
+              `torch.flip(frame, [3])` (:200-206) -> NCHW-logical [N,3,H,W] tensor of `dtype` in NHWC storage.
+    seg_u8    uint8 [N,H,W] class ids (src/folder.py:95-96): `.long()` labels [N,H,W] (:100), `.float()` class maps
+              [N,1,H,W] (:97-99), one-hot layout [N,K,H,W] (`transform_seg_one_hot`, src/models/net_utils.py:14-24), flipped
+              along W with the frames.
+    Returns a dict with the requested entries among 'frames', 'label', 'seg_float', 'one_hot'."""
+    dev = _require_cuda(frames_u8, seg_u8)
+    if frames_u8 is None and seg_u8 is None:
+        raise VlgError("ingest needs frames_u8 and / or seg_u8")
+    ref = frames_u8 if frames_u8 is not None else seg_u8
+    N, H, W = ref.shape[0], ref.shape[1], ref.shape[2]
+    _expect(frames_u8, (N, H, W, 3), "frames_u8", torch.uint8)
+    _expect(seg_u8, (N, H, W), "seg_u8", torch.uint8)
+    prob = _problem(N, H, W, n_classes, dtype, WarpLossConfig())
+    out = {}
+    f_in = frames_u8.contiguous() if frames_u8 is not None else None
+    s_in = seg_u8.contiguous() if seg_u8 is not None else None
+    if f_in is not None:
+        out["frames"] = empty_nhwc((N, 3, H, W), dtype, dev)
+    if s_in is not None:
+        if want_label:
+            out["label"] = torch.empty((N, H, W), dtype=torch.int64, device=dev)
+        if want_seg_float:
+            out["seg_float"] = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev)
+        if want_one_hot:
+            out["one_hot"] = empty_nhwc((N, n_classes, H, W), dtype, dev)
+        if not (want_label or want_seg_float or want_one_hot):
+            raise VlgError("seg_u8 given but no output requested for it")
+    m3 = (C.c_float * 3)(*[float(v) for v in mean]) if mean is not None else None
+    s3 = (C.c_float * 3)(*[float(v) for v in std]) if mean is not None else None
+    with torch.cuda.device(dev):
+        check(_cabi.load().vlg_ingest(C.byref(prob), _ptr(f_in), m3, s3, int(flip), _ptr(out.get("frames")), _ptr(s_in),
+                                      _ptr(out.get("label")), _ptr(out.get("seg_float")), _ptr(out.get("one_hot")), None, _stream()))
+    return out
 
 
 def rollout(img: torch.Tensor, label: torch.Tensor, flow_fn, steps: int = 5, *, padding_mode: str = "border"):
@@ -298,14 +397,16 @@ class _WarpLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src_rgb, src_layout, coords, tgt_rgb, tgt_label, cfg: WarpLossConfig):
         lib = _cabi.load()
-        _require_cuda(src_rgb, src_layout, coords, tgt_rgb, tgt_label)
+        dev = _require_cuda(src_rgb, src_layout, coords, tgt_rgb, tgt_label)
+        if src_rgb.dim() != 4 or src_layout.dim() != 4:
+            raise VlgError("src_rgb / src_layout must be NCHW-logical 4-d tensors")
         N, _, H, W = src_rgb.shape
         K = src_layout.shape[1]
-        dev, dt = src_rgb.device, src_rgb.dtype
-        if src_layout.dtype != dt or tgt_rgb.dtype != dt:
-            raise VlgError("src_rgb, src_layout and tgt_rgb must share one dtype")
-        if tgt_label.dtype != torch.int64 or tuple(tgt_label.shape) != (N, H, W):
-            raise VlgError("tgt_label must be int64 [N,H,W] (src/folder.py:100)")
+        dt = src_rgb.dtype
+        _expect(src_rgb, (N, 3, H, W), "src_rgb")
+        _expect(src_layout, (N, K, H, W), "src_layout", dt)
+        _expect(tgt_rgb, (N, 3, H, W), "tgt_rgb", dt)
+        _expect(tgt_label, (N, H, W), "tgt_label (src/folder.py:100)", torch.int64)
         prob = _problem(N, H, W, K, dt, cfg)
         need_c, need_a, need_b = ctx.needs_input_grad[2], ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_src = need_a or need_b
@@ -319,11 +420,13 @@ class _WarpLossFn(torch.autograd.Function):
         d_a = empty_nhwc(a.shape, dt, dev) if need_src else None
         d_b = empty_nhwc(b.shape, dt, dev) if need_src else None
         arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if cfg.want_argmax else None
-        check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(c), _ptr(t), _ptr(lab), _ptr(loss),
-                                        _ptr(d_c), _ptr(d_a), _ptr(d_b), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
+        with torch.cuda.device(dev):
+            check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(c), _ptr(t), _ptr(lab), _ptr(loss),
+                                            _ptr(d_c), _ptr(d_a), _ptr(d_b), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
+            if cfg.debug:
+                _check_status(ws, cfg)
         ctx.grads = (d_a if need_a else None, d_b if need_b else None, d_c if need_c else None)
         ctx.consumed = False
-        ctx.workspace = ws  # holds the status word; freed with the graph
         total = loss[_cabi.LOSS_TOTAL].clone()   # own storage: `loss` itself is returned non-differentiable
         ctx.mark_non_differentiable(*([loss] if arg is None else [loss, arg]))  # one call only
         return total, loss, arg
@@ -336,15 +439,77 @@ class _WarpLossFn(torch.autograd.Function):
         lib = _cabi.load()
         d_a, d_b, d_c = ctx.grads
         g = g_total.detach().to(torch.float32).contiguous()
-        for t in (d_a, d_b, d_c):
-            if t is not None:
-                check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
+        with torch.cuda.device(g.device):
+            for t in (d_a, d_b, d_c):
+                if t is not None:
+                    check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
         return d_a, d_b, d_c, None, None, None
+
+
+class _WarpLossLabelsFn(torch.autograd.Function):
+    """The fused op with a LABEL layout source (sources are data: the gradient goes to the coordinates only)."""
+
+    @staticmethod
+    def forward(ctx, src_rgb, src_label, coords, tgt_rgb, tgt_label, cfg: WarpLossConfig, n_classes: int):
+        lib = _cabi.load()
+        dev = _require_cuda(src_rgb, src_label, coords, tgt_rgb, tgt_label)
+        if src_label.dim() != 3 or src_label.dtype != torch.int64:
+            raise VlgError("src_label must be int64 [N,H,W] class ids")
+        N, H, W = src_label.shape
+        dt = src_rgb.dtype if src_rgb is not None else torch.float32
+        _expect(src_rgb, (N, 3, H, W), "src_rgb")
+        _expect(tgt_rgb, (N, 3, H, W), "tgt_rgb", dt)
+        _expect(tgt_label, (N, H, W), "tgt_label (src/folder.py:100)", torch.int64)
+        if (src_rgb is None) != (tgt_rgb is None):
+            raise VlgError("src_rgb and tgt_rgb go together")
+        prob = _problem(N, H, W, n_classes, dt, cfg)
+        need_c = ctx.needs_input_grad[2]
+        a = to_nhwc(src_rgb) if src_rgb is not None else None
+        t = to_nhwc(tgt_rgb) if tgt_rgb is not None else None
+        c = _coords(coords, N, H, W)
+        ws = _workspace(prob, False, dev)
+        loss = torch.empty(_cabi.LOSS_SLOTS, dtype=torch.float32, device=dev)
+        d_c = torch.empty_like(c) if need_c else None
+        arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if cfg.want_argmax else None
+        with torch.cuda.device(dev):
+            check(lib.vlg_warp_loss_labels_fwd_bwd(C.byref(prob), _ptr(a), _ptr(src_label.contiguous()), _ptr(c), _ptr(t),
+                                                   _ptr(tgt_label.contiguous()), _ptr(loss), _ptr(d_c), _ptr(arg), _ptr(ws),
+                                                   ws.numel(), _stream()))
+            if cfg.debug:
+                _check_status(ws, cfg)
+        ctx.grad_c = d_c
+        ctx.consumed = False
+        total = loss[_cabi.LOSS_TOTAL].clone()
+        ctx.mark_non_differentiable(*([loss] if arg is None else [loss, arg]))
+        return total, loss, arg
+
+    @staticmethod
+    def backward(ctx, g_total, g_loss, g_arg):
+        if ctx.consumed:
+            raise VlgError("the fused warp-loss gradients were already consumed (retain_graph is unsupported)")
+        ctx.consumed = True
+        d_c = ctx.grad_c
+        if d_c is not None:
+            g = g_total.detach().to(torch.float32).contiguous()
+            with torch.cuda.device(g.device):
+                check(_cabi.load().vlg_scale_grads(_ptr(d_c), d_c.numel(), _cabi.F32, _ptr(g), _stream()))
+        return None, None, d_c, None, None, None, None
+
+
+def warp_loss_labels(src_rgb, src_label, coords, tgt_rgb, tgt_label, cfg: Optional[WarpLossConfig] = None, n_classes: int = 20):
+    """`warp_loss` with the layout source given as the int64 class-id map [N,H,W] the reference's dataset holds
+    (it stands for one_hot(src_label), src/models/net_utils.py:14-24): same losses, argmax bit-exact with the dense
+    path, 8 B/px of layout traffic instead of 80, differentiable w.r.t. coords only (the sources are data).
+    Returns (total, loss_vector[LOSS_SLOTS], argmax | None)."""
+    return _WarpLossLabelsFn.apply(src_rgb, src_label, coords, tgt_rgb, tgt_label, cfg or WarpLossConfig(), n_classes)
 
 
 def warp_loss(src_rgb, src_layout, coords, tgt_rgb, tgt_label, cfg: Optional[WarpLossConfig] = None):
     """Returns (total, loss_vector[LOSS_SLOTS], argmax | None).  `total` is differentiable w.r.t.
-    coords (flow / grid), src_rgb and src_layout."""
+    coords (flow / grid), src_rgb and src_layout.  An int64 [N,H,W] `src_layout` is a label source
+    (see warp_loss_labels)."""
+    if src_layout is not None and src_layout.dim() == 3 and src_layout.dtype == torch.int64:
+        return warp_loss_labels(src_rgb, src_layout, coords, tgt_rgb, tgt_label, cfg)
     return _WarpLossFn.apply(src_rgb, src_layout, coords, tgt_rgb, tgt_label, cfg or WarpLossConfig())
 
 
@@ -356,11 +521,18 @@ class _PixelLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, out_rgb, tgt_rgb, logits, tgt_label, cfg: WarpLossConfig):
         lib = _cabi.load()
-        _require_cuda(out_rgb, tgt_rgb, logits, tgt_label)
+        dev = _require_cuda(out_rgb, tgt_rgb, logits, tgt_label)
         ref = out_rgb if out_rgb is not None else logits
+        if ref is None or ref.dim() != 4:
+            raise VlgError("expected NCHW-logical 4-d tensors")
         N, _, H, W = ref.shape
         K = logits.shape[1] if logits is not None else 20
-        dev, dt = ref.device, ref.dtype
+        dt = ref.dtype
+        _expect(out_rgb, (N, 3, H, W), "output rgb")
+        _expect(tgt_rgb, (N, 3, H, W), "target rgb")
+        _expect(logits, (N, K, H, W), "logits", dt)
+        if (out_rgb is None) != (tgt_rgb is None) or (logits is None) != (tgt_label is None):
+            raise VlgError("(output, target) go together")
         prob = _problem(N, H, W, K, dt, cfg)
         need_a = out_rgb is not None and ctx.needs_input_grad[0]
         need_z = logits is not None and ctx.needs_input_grad[2]
@@ -375,8 +547,11 @@ class _PixelLossFn(torch.autograd.Function):
         d_a = empty_nhwc(a.shape, dt, dev) if need_a else None
         d_z = empty_nhwc(z.shape, dt, dev) if need_z else None
         arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if (cfg.want_argmax and z is not None) else None
-        check(lib.vlg_pixel_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(t), _ptr(z), _ptr(lab), _ptr(loss), _ptr(d_a),
-                                         _ptr(d_z), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
+        with torch.cuda.device(dev):
+            check(lib.vlg_pixel_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(t), _ptr(z), _ptr(lab), _ptr(loss), _ptr(d_a),
+                                             _ptr(d_z), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
+            if cfg.debug:
+                _check_status(ws, cfg)
         ctx.grads = (d_a, d_z)
         ctx.consumed = False
         ctx.mark_non_differentiable(*([loss] if arg is None else [loss, arg]))  # one call only
@@ -390,9 +565,10 @@ class _PixelLossFn(torch.autograd.Function):
         lib = _cabi.load()
         d_a, d_z = ctx.grads
         g = g_total.detach().to(torch.float32).contiguous()
-        for t in (d_a, d_z):
-            if t is not None:
-                check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
+        with torch.cuda.device(g.device):
+            for t in (d_a, d_z):
+                if t is not None:
+                    check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
         return d_a, None, d_z, None, None
 
 
@@ -404,5 +580,6 @@ def pixel_losses(out_rgb, tgt_rgb, logits, tgt_label, cfg: Optional[WarpLossConf
 def read_status(workspace: torch.Tensor) -> int:
     """Synchronising debug helper: VLG_STATUS_* bits left by the last pass on this workspace."""
     st = C.c_uint32(0)
-    check(_cabi.load().vlg_read_status(_ptr(workspace), workspace.numel(), C.byref(st), _stream()))
+    with torch.cuda.device(workspace.device):
+        check(_cabi.load().vlg_read_status(_ptr(workspace), workspace.numel(), C.byref(st), _stream()))
     return st.value
