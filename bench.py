@@ -2,23 +2,31 @@
 """bench.py -- headline benchmark of the hot path (BASELINE.json: warp+loss fwd/bwd Mpixel/s and
 HBM GB/s vs peak) on N GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c5|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c1|c3|c4|c5] [--batch B] [--no-sweep] ...
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the fused op over one batch of synthetic Cityscapes-shaped input
-(BASELINE.json configs[1]: 16x256x512, K=20, fp32): flow-guided warp of RGB + layout, all loss
-terms, gradients to flow, src_rgb and src_layout.  Weak scaling: every rank processes one such
-batch; the only exchange is one NCCL all-reduce of the 8-float loss vector.
+A "step" is one pass of the hot path over one batch of synthetic input.  Workloads = BASELINE.json configs:
+  c2 (default)  16x256x512, K=20, fp32: flow-guided warp of RGB + layout, all loss terms, gradients to flow, src_rgb and
+                src_layout (220 algorithmic B/px).  Weak scaling: every rank processes one such batch; the only exchange
+                is one NCCL all-reduce of the 8-float loss vector.
+  c1            2x128x256 (the reference's CPU-runnable case; L2-resident, launch-bound)
+  c3            8x1024x2048 bf16 (122 B/px)
+  c4            5-step autoregressive rollout at 512x1024, GLOBAL batch 32 split over the ranks (strong scaling),
+                label layouts fed back (48 B/px per step)
+  c5            Bx375x1242, sigma = 48 px + 5 % outliers (large displacement); --batch B, default 16
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the
-public module API from pinned host buffers, `roofline` is live CUDA-event timing of the dominant
-kernel against MEASURED_PEAKS.json, `cpu_baseline` is the oracle port on the host cores.
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the public module API from
+pinned host buffers holding what the dataset holds (uint8 frames and class maps, fp32 flow), `roofline` is the
+longest kernel of the step timed by CUDA events on its launch stream against MEASURED_PEAKS.json, `cpu_baseline` is
+the oracle port on the host cores, `sweep` carries the other BASELINE configs (C3, C4, C5 batch sweep) in compact form.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -36,11 +44,21 @@ WORKLOADS = {
     "c1": (2, 128, 256, 20, 4.0, 0.0, "f32"),
     "c2": (16, 256, 512, 20, 4.0, 0.0, "f32"),
     "c2calm": (16, 256, 512, 20, 0.5, 0.0, "f32"),    # tuning: same shape, flow so small that no tap leaves the staged windows
+    "c2q": (4, 256, 512, 20, 4.0, 0.0, "f32"),        # tuning: a quarter of c2 (pass 1's staging, 54 MB, stays in the L2 for pass 2)
     "c3": (8, 1024, 2048, 20, 4.0, 0.0, "bf16"),
+    "c4": (32, 512, 1024, 20, 4.0, 0.0, "f32"),       # rollout: GLOBAL batch, 5 steps
     "c5": (16, 375, 1242, 20, 48.0, 0.05, "f32"),
 }
-BYTES_PER_PX = {"f32": dict(step=220, pass1=128, pass2=92), "bf16": dict(step=122, pass1=76, pass2=46)}
+ROLLOUT_STEPS = 5
+# algorithmic bytes per output pixel: each input element read once, each required
+# output written once.  Per kernel: rgb strip = coords 8 + src_rgb 12 + tgt_rgb 12; layout tile = src_layout 80 + label 8
+# + d_flow 8; pass 2 = d_src_rgb 12 + d_src_layout 80 (bf16: activations and their gradients halve).
+BYTES_PER_PX = {"f32": dict(step=220, pass1=128, rgb_strip=32, lay_tile=96, pass2=92),
+                "bf16": dict(step=122, pass1=76, rgb_strip=20, lay_tile=56, pass2=46)}
+ROLLOUT_BYTES_PER_PX = 48      # per rollout step: coords 8 + rgb 12 + label 8 read, rgb 12 + label 8 written
 FALLBACK_HBM_GBS = 6650.0
+MIN_TIMED_MS = 250.0           # the timed region lasts at least this long whatever --steps says
+REF_SAMPLE_IMAGES = 2          # bounded sample of the CPU arms (cpu_baseline and --impl reference alike)
 
 
 def make_inputs(N, H, W, K, sigma, far, dtype, device, seed=1024):
@@ -75,6 +93,20 @@ def make_inputs(N, H, W, K, sigma, far, dtype, device, seed=1024):
     return out
 
 
+def make_inputs_tiled(N, H, W, K, sigma, far, dtype, device, seed):
+    """Batches larger than 16 are the 16-image synthetic batch repeated with rolled sample order (the host-side
+    generator is the slow part; throughput does not depend on which samples repeat)."""
+    base = make_inputs(min(N, 16), H, W, K, sigma, far, dtype, device, seed)
+    if N <= 16:
+        return base
+    reps = (N + 15) // 16
+    out = {}
+    for k, v in base.items():
+        t = torch.cat([v.roll(r, 0) for r in range(reps)], 0)[:N]
+        out[k] = t.contiguous(memory_format=torch.channels_last) if k in ("src_rgb", "tgt_rgb", "src_layout") else t.contiguous()
+    return out
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -86,7 +118,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -97,10 +129,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi takes a moment to start: do not begin the timed region before its first sample."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.rows.clear()      # samples from before the timed region do not count
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -114,52 +152,440 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_oracle_throughput(N, H, W, K, sigma, far, n_sample, iters):
-    """Oracle port (torch CPU composition of the reference's losses + grid_sample) on a bounded
-    sample of the workload: fwd+bwd to flow, src_rgb, src_layout.  Returns Mpixel/s."""
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_oracle_run(wl, N, steps, warmup):
+    """The reference's own CPU implementation of the path: it is pure Python / PyTorch with no compiled code of its
+    own, so this is the oracle port (oracle/torch_oracle.py) on the host cores, all threads.  One step = fwd+bwd
+    (rollout: 5 warps with argmax feedback) on a bounded sample of REF_SAMPLE_IMAGES images of the workload.
+    Returns (Mpixel/s, mean seconds per step, description)."""
     from oracle import torch_oracle as TO
+    _, H, W, K, sigma, far, dtype = WORKLOADS[wl]
+    n_sample = min(N, REF_SAMPLE_IMAGES)
     d = make_inputs(n_sample, H, W, K, sigma, far, "f32", None)
+    if wl == "c4":
+        flows = [make_inputs(n_sample, H, W, K, sigma, 0.0, "f32", None, seed=78 + t)["flow"] for t in range(ROLLOUT_STEPS)]
+        lab0 = d["src_layout"].argmax(1)
+
+        def one():
+            img, lab = d["src_rgb"], lab0
+            with torch.no_grad():
+                for t in range(ROLLOUT_STEPS):
+                    grid = TO.flow_to_grid(flows[t])
+                    img = TO.warp(img, grid)
+                    lab = TO.warp(TO.one_hot_layout(lab, K), grid).argmax(1)     # src/trainer.py:461,467
+            return lab
+        px = n_sample * H * W * ROLLOUT_STEPS
+        what = f"{n_sample}x{H}x{W} x{ROLLOUT_STEPS} rollout steps (dense one-hot feedback, src/trainer.py:460-469)"
+    else:
+        def one():
+            return TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"], w_tv=0.5)
+        px = n_sample * H * W
+        what = f"{n_sample}x{H}x{W} slice of the batch, fwd+bwd (grads to flow, src_rgb, src_layout)"
     ts = []
-    for i in range(iters + 1):
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"], w_tv=0.5)
-        ts.append(time.perf_counter() - t0)
-    ts = sorted(ts[1:])  # first call = warm-up
-    t = ts[len(ts) // 2]
-    return n_sample * H * W / t / 1e6, t
+        one()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    return px / t / 1e6, t, f"{what}; torch CPU oracle port, mean of {len(ts)} after {warmup} warm-up ({t * 1e3:.0f} ms/step)"
+
+
+def workload_config(wl, N, world, dtype, with_src=True):
+    _, H, W, K, _, _, _ = WORKLOADS[wl]
+    if wl == "c4":
+        return {"workload": f"c4: {ROLLOUT_STEPS}-step autoregressive rollout at {H}x{W}, global batch {N}, K={K} {dtype}, label layouts fed back",
+                "global_batch": N, "parallelism": f"dp{world}"}
+    return {"workload": f"{wl}: {N}x{H}x{W} K={K} {dtype} warp+loss fwd+bwd per GPU" + ("" if with_src else " (flow-grad only)"),
+            "per_gpu_pixels": N * H * W, "grads": "flow,src_rgb,src_layout" if with_src else "flow", "parallelism": f"dp{world}"}
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
-    pure Python/PyTorch with no compiled code of its own, so this is the oracle port
-    (oracle/torch_oracle.py) on the box's host cores, all threads."""
+    """`--impl reference`: rank 0 alone runs the CPU arm on the same workload description as our arm."""
     if rank != 0:
         return
-    N, H, W, K, sigma, far, dtype = WORKLOADS[args.workload]
-    n_sample = min(N, 2)
-    ts = []
     try:   # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread it may
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         pass
-    from oracle import torch_oracle as TO
-    d = make_inputs(n_sample, H, W, K, sigma, far, "f32", None)
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"], w_tv=0.5)
-        if i >= args.warmup:
-            ts.append(time.perf_counter() - t0)
-    t = sum(ts) / len(ts)
-    val = n_sample * H * W / t / 1e6
-    sample = f"{n_sample}x{H}x{W} slice of the {N}x{H}x{W} batch per step, torch CPU oracle port, fwd+bwd"
+    N0, H, W, K, sigma, far, dtype = WORKLOADS[args.workload]
+    N = args.batch or N0
+    val, t, sample = cpu_oracle_run(args.workload, N, args.steps, max(args.warmup, 1))
     print(json.dumps({
         "impl": "reference", "metric": "warp+loss fwd/bwd throughput", "value": val, "unit": "Mpixel/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {N}x{H}x{W} K={K} fp32 fwd+bwd (bounded sample {n_sample}x{H}x{W} per step)"},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.workload, N, world, dtype, not args.flow_grad_only),
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+class Ctx:
+    """Process-wide handles of the GPU arm."""
+
+    def __init__(self):
+        import vlg_b200
+        from vlg_b200 import _cabi, ops
+        self.vlg, self.cabi, self.ops = vlg_b200, _cabi, ops
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group(backend="nccl", device_id=self.dev)
+            self.dist = dist
+        self.lib = _cabi.load()
+        self.stream = torch.cuda.current_stream()
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def timed(self, step, steps, min_ms=MIN_TIMED_MS):
+        """EXACTLY `steps` step groups of `r` passes each between barrier + synchronize on both sides; `r` is chosen
+        so that the region lasts >= min_ms.  Returns (ms per pass, max over ranks; r; ms of the whole region)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        for i in range(4):
+            step(i)
+        e1.record(self.stream)
+        self.barrier()
+        est_ms = self.max_over_ranks(e0.elapsed_time(e1) / 4)
+        r = max(1, int(math.ceil(min_ms / max(est_ms * steps, 1e-6))))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        for i in range(steps * r):
+            step(i)
+        e1.record(self.stream)
+        self.barrier()
+        total = self.max_over_ranks(e0.elapsed_time(e1))
+        return total / (steps * r), r, total
+
+
+class Fused:
+    """Device-resident fused warp+loss step of one workload: two alternating input sets (no step re-reads lines its
+    predecessor left in L2), gradient buffers, workspace, CUDA graphs of the launch sequence."""
+
+    def __init__(self, cx: Ctx, wl, N, with_src=True, use_graph=True, seed=1024):
+        _, H, W, K, sigma, far, dtype = WORKLOADS[wl]
+        self.cx, self.wl, self.N, self.H, self.W, self.K, self.dtype = cx, wl, N, H, W, K, dtype
+        self.P = N * H * W
+        self.with_src = with_src
+        ops, cabi = cx.ops, cx.cabi
+        tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+        self.tdt = tdt
+        n_sets = 2 if self.P * 120 < 3e9 else 1       # large batches exceed the L2 many times over by themselves
+        self.sets = [make_inputs_tiled(N, H, W, K, sigma, far, dtype, cx.dev, seed=seed + 7 * cx.rank + s) for s in range(n_sets)]
+        cfg = ops.WarpLossConfig(w_tv=0.5)
+        self.prob = ops._problem(N, H, W, K, tdt, cfg)
+        self.ws = ops._workspace(self.prob, with_src, cx.dev, cached=False)
+        self.loss = torch.zeros(cabi.LOSS_SLOTS, dtype=torch.float32, device=cx.dev)
+        self.d_c = torch.empty(N, H, W, 2, dtype=torch.float32, device=cx.dev)
+        self.d_a = ops.empty_nhwc((N, 3, H, W), tdt, cx.dev) if with_src else None
+        self.d_b = ops.empty_nhwc((N, K, H, W), tdt, cx.dev) if with_src else None
+        self.graphs = None
+        self.launches_per_step = None
+        for i in range(3):
+            self.step(i)
+        cx.barrier()
+        if use_graph:
+            self._capture()
+
+    # ---- launch sequences through the C ABI
+    def _sp(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch_fused(self, s, sp):
+        ptr, lib, ops = self.cx.ops._ptr, self.cx.lib, self.cx.ops
+        ops.check(lib.vlg_warp_loss_fwd_bwd(C.byref(self.prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
+                                            ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(self.loss), ptr(self.d_c), ptr(self.d_a),
+                                            ptr(self.d_b), None, ptr(self.ws), self.ws.numel(), sp))
+
+    def launch_pass1(self, s, sp):
+        ptr, lib, ops = self.cx.ops._ptr, self.cx.lib, self.cx.ops
+        ops.check(lib.vlg_warp_loss_pass1(C.byref(self.prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
+                                          ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(self.loss), ptr(self.d_c), None,
+                                          int(self.with_src), ptr(self.ws), self.ws.numel(), sp))
+
+    def launch_pass2(self, s, sp):
+        if self.with_src:
+            ptr, lib, ops = self.cx.ops._ptr, self.cx.lib, self.cx.ops
+            ops.check(lib.vlg_warp_bwd_src(C.byref(self.prob), ptr(s["flow"]), ptr(self.d_a), ptr(self.d_b), ptr(self.ws),
+                                           self.ws.numel(), sp))
+
+    def _capture(self):
+        cx = self.cx
+        try:
+            n_before = cx.vlg.launch_count()
+            gs = []
+            for s in self.sets:
+                if cx.dist is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self.launch_fused(s, self._sp())
+                    gs.append(g)
+                else:   # two graphs per input set: the all-reduce is issued between them
+                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        self.launch_pass1(s, self._sp())
+                    with torch.cuda.graph(g2):
+                        self.launch_pass2(s, self._sp())
+                    gs.append((g1, g2))
+            self.launches_per_step = (cx.vlg.launch_count() - n_before) // len(self.sets)
+            self.graphs = gs
+            for i in range(4):
+                self.step(i)
+            cx.barrier()
+        except Exception as exc:   # capture unsupported: plain launches
+            print(f"[bench] CUDA graph capture failed ({exc}); using plain launches", file=sys.stderr)
+            self.graphs = None
+
+    def step(self, i):
+        """One pass of the hot path (the last pass-1 CTA reduces the loss vector).  Data parallel: the loss vector is
+        complete after pass 1, so the path's only exchange -- one all-reduce of 8 floats -- is issued there and
+        overlaps pass 2."""
+        cx = self.cx
+        k = i % len(self.sets)
+        s = self.sets[k]
+        sp = C.c_void_p(cx.stream.cuda_stream)
+        if cx.dist is not None:
+            if self.graphs is not None: self.graphs[k][0].replay()
+            else: self.launch_pass1(s, sp)
+            work = cx.dist.all_reduce(self.loss, async_op=True)
+            if self.graphs is not None: self.graphs[k][1].replay()
+            else: self.launch_pass2(s, sp)
+            work.wait()
+        elif self.graphs is not None:
+            self.graphs[k].replay()
+        else:
+            self.launch_fused(s, sp)
+
+    def count_launches(self, n_steps):
+        if self.graphs is not None:
+            return self.launches_per_step * n_steps     # replayed from the graph: the host counter does not move
+        n0 = self.cx.vlg.launch_count()
+        self.step(0)
+        torch.cuda.synchronize()
+        return (self.cx.vlg.launch_count() - n0) * n_steps
+
+    def kernel_times(self, reps=20):
+        """Median device time of the three main kernels inside the real (direct) launch sequence: CUDA events recorded
+        by the library on the launch stream right around each kernel (vlg_timeline_arm / vlg_timeline_read)."""
+        cx = self.cx
+        sp = C.c_void_p(cx.stream.cuda_stream)
+        rows = []
+        ms4 = (C.c_float * 4)()
+        cx.barrier()
+        for i in range(reps):
+            cx.ops.check(cx.lib.vlg_timeline_arm(1))
+            self.launch_fused(self.sets[i % len(self.sets)], sp)
+            cx.ops.check(cx.lib.vlg_timeline_arm(0))
+            cx.ops.check(cx.lib.vlg_timeline_read(ms4))
+            rows.append(list(ms4))
+        med = lambda j: sorted(r[j] for r in rows)[len(rows) // 2]
+        return {"rgb_strip_kernel": med(0), "lay_tile_kernel": med(1), "pass2_rec_kernel": med(2), "span_first_to_last": med(3)}
+
+    def cupti_table(self, n=10):
+        try:
+            from torch.profiler import profile, ProfilerActivity
+            sp = C.c_void_p(self.cx.stream.cuda_stream)
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for i in range(n):
+                    self.launch_fused(self.sets[i % len(self.sets)], sp)
+                torch.cuda.synchronize()
+            return {e.key.split("(")[0].replace("void ", "").replace("vlg::", ""): round(e.device_time_total / n, 2)
+                    for e in prof.key_averages() if e.device_time_total > 0}
+        except Exception as exc:   # profiler unavailable: the event timings stand on their own
+            return {"unavailable": str(exc)}
+
+    def free(self):
+        self.graphs = None
+        self.sets = None
+        self.ws = self.d_a = self.d_b = self.d_c = None
+        torch.cuda.empty_cache()
+
+
+def u8_host_inputs(d, K):
+    """What the reference's dataset holds for one batch (src/folder.py:85-104): uint8 RGB frames [N,H,W,3], uint8
+    class maps [N,H,W]; plus the fp32 flow the op consumes.  16 bytes per pixel."""
+    mean = torch.tensor([0.485, 0.456, 0.406], device=d["src_rgb"].device)[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225], device=d["src_rgb"].device)[None, :, None, None]
+    to_u8 = lambda x: ((x.float() * std + mean) * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    host = {
+        "src_u8": to_u8(d["src_rgb"]), "tgt_u8": to_u8(d["tgt_rgb"]),
+        "src_seg_u8": d["src_layout"].argmax(1).to(torch.uint8), "tgt_seg_u8": d["tgt_label"].to(torch.uint8),
+        "flow": d["flow"],
+    }
+    return {k: v.cpu().pin_memory() for k, v in host.items()}
+
+
+def e2e_fused(cx: Ctx, fz: Fused, steps):
+    """End to end through the public API (vlg_b200.ingest + vlg_b200.WarpLoss + backward) from pinned host memory.
+    Every step uploads one full input set -- what the dataset holds: uint8 frames and class maps, fp32 flow -- and reads
+    the step's loss vector back.  Double-buffered: the inputs of step i+1 travel on a copy stream while step i
+    computes (what a DataLoader prefetcher does)."""
+    vlg, dev, stream = cx.vlg, cx.dev, cx.stream
+    host = u8_host_inputs(fz.sets[0], fz.K)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    crit = vlg.WarpLoss(weights=(40.0, 20.0, 10.0, 0.5))
+    copy_stream = torch.cuda.Stream(device=dev)
+    dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    up_done = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(j):
+        copy_stream.wait_event(consumed[j])      # the step that read this buffer set has finished with it
+        with torch.cuda.stream(copy_stream):
+            for k, v in host.items():
+                dbuf[j][k].copy_(v, non_blocking=True)
+            up_done[j].record(copy_stream)
+
+    def e2e_step(i):
+        j = i & 1
+        upload(j ^ 1)                      # inputs of the NEXT step
+        stream.wait_event(up_done[j])
+        cur = dbuf[j]
+        src = vlg.ingest(cur["src_u8"], cur["src_seg_u8"], n_classes=fz.K, dtype=fz.tdt, want_label=False, want_one_hot=True)
+        tgt = vlg.ingest(cur["tgt_u8"], cur["tgt_seg_u8"], n_classes=fz.K, dtype=fz.tdt, want_label=True)
+        a = src["frames"].requires_grad_(fz.with_src)
+        b = src["one_hot"].requires_grad_(fz.with_src)
+        f = cur["flow"].detach().requires_grad_(True)
+        total = crit(a, b, f, tgt["frames"], tgt["label"])
+        total.backward()
+        consumed[j].record(stream)
+        return crit.last_terms.cpu()       # device -> host read of the step's result (synchronises)
+
+    for j in range(2):
+        consumed[j].record(stream)
+    upload(0)
+    for i in range(4):
+        e2e_step(i)
+    cx.barrier()
+    n = max(4, min(steps, 20)) & ~1
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(n):
+        e2e_step(i)
+    e1.record(stream)
+    cx.barrier()
+    ms = cx.max_over_ranks(e0.elapsed_time(e1) / n)
+    return {"value": cx.world * fz.P / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": cx.cabi.LOSS_SLOTS * 4, "ms_per_step": ms, "steps": n,
+            "inputs": "pinned host, what the dataset holds (src/folder.py:85-104): uint8 RGB frames [N,H,W,3] x2, uint8 class maps "
+                      "[N,H,W] x2, fp32 flow = 16 B/px; on the device vlg_ingest turns them into normalised NHWC frames, int64 "
+                      "labels and the one-hot source layout (ToTensor + renorm + one_hot, bit-identical), then WarpLoss + "
+                      "backward; the loss vector is read back every step; double-buffered uploads on a copy stream"}
+
+
+class Rollout:
+    """BASELINE config 4: 5 autoregressive steps with LABEL layout sources fed back (vlg_warp_fwd_labels),
+    per-rank batch = global batch / world (the rollout of a sample is independent of every other sample)."""
+
+    def __init__(self, cx: Ctx, n_rank, seed=77):
+        _, H, W, K, sigma, _, _ = WORKLOADS["c4"]
+        self.cx, self.n, self.H, self.W, self.K = cx, n_rank, H, W, K
+        d = make_inputs_tiled(n_rank, H, W, K, sigma, 0.0, "f32", cx.dev, seed=seed + cx.rank)
+        self.img = d["src_rgb"]
+        self.lab = d["src_layout"].argmax(1)
+        self.flows = [make_inputs_tiled(min(n_rank, 4), H, W, K, sigma, 0.0, "f32", cx.dev, seed=seed + 1 + t)["flow"] for t in range(ROLLOUT_STEPS)]
+        if n_rank > 4:   # flows of larger per-rank batches: the 4-image flow set repeated (throughput does not depend on it)
+            self.flows = [torch.cat([f.roll(r, 0) for r in range((n_rank + 3) // 4)], 0)[:n_rank].contiguous() for f in self.flows]
+        self.px_steps = n_rank * H * W * ROLLOUT_STEPS
+        del d
+
+    def step(self, i=0):
+        return self.cx.vlg.rollout(self.img, self.lab, lambda t, im, lb: self.flows[t], steps=ROLLOUT_STEPS)
+
+    def e2e(self, steps):
+        """Uploads the uint8 start frame + class map and the five fp32 flows, rolls out, reads the final class map back
+        as uint8."""
+        cx = self.cx
+        mean = torch.tensor([0.485, 0.456, 0.406], device=cx.dev)[None, :, None, None]
+        std = torch.tensor([0.229, 0.224, 0.225], device=cx.dev)[None, :, None, None]
+        host = {"img_u8": ((self.img * std + mean) * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().pin_memory(),
+                "seg_u8": self.lab.to(torch.uint8).cpu().pin_memory()}
+        for t in range(ROLLOUT_STEPS):
+            host[f"flow{t}"] = self.flows[t].cpu().pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        buf = {k: torch.empty_like(v, device=cx.dev) for k, v in host.items()}
+        out_host = torch.empty(self.n, self.H, self.W, dtype=torch.uint8).pin_memory()
+
+        def one():
+            for k, v in host.items():
+                buf[k].copy_(v, non_blocking=True)
+            ing = cx.vlg.ingest(buf["img_u8"], buf["seg_u8"], n_classes=self.K, want_label=True)
+            _, labs = cx.vlg.rollout(ing["frames"], ing["label"], lambda t, im, lb: buf[f"flow{t}"], steps=ROLLOUT_STEPS)
+            out_host.copy_(labs[-1].to(torch.uint8), non_blocking=True)
+            torch.cuda.synchronize()
+        for _ in range(2):
+            one()
+        cx.barrier()
+        n = max(2, min(steps, 6))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cx.stream)
+        for _ in range(n):
+            one()
+        e1.record(cx.stream)
+        cx.barrier()
+        ms = cx.max_over_ranks(e0.elapsed_time(e1) / n)
+        return {"value": cx.world * self.px_steps / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": out_host.numel(), "ms_per_step": ms, "steps": n,
+                "inputs": "pinned host: uint8 start frame + class map, five fp32 flows; vlg_ingest + 5 x vlg_warp_fwd_labels; the final "
+                          "class map is read back as uint8"}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth, burst)"
+    return FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on the c2 workload, from the committed
+    `ncu --set full` capture (newest profiles/rNN_ncu_traffic.json)."""
+    pdir = os.path.join(ROOT, "profiles")
+    cands = sorted(f for f in os.listdir(pdir) if f.endswith("_ncu_traffic.json")) if os.path.isdir(pdir) else []
+    for f in reversed(cands):
+        k = json.load(open(os.path.join(pdir, f))).get("kernels", {}).get(kernel)
+        if k:
+            return k["dram_bytes_read"] + k["dram_bytes_write"], f
+    return None, None
+
+
+def sweep_entry(cx, wl, N, steps, peak, note=None):
+    """Compact line of another BASELINE config: device-resident step time + fraction of its own HBM roofline."""
+    _, H, W, K, _, _, dtype = WORKLOADS[wl]
+    try:
+        fz = Fused(cx, wl, N, with_src=True)
+        ms, r, total = cx.timed(fz.step, steps, min_ms=120.0)
+        kt = fz.kernel_times(reps=5) if cx.world == 1 else None
+        bpp = BYTES_PER_PX[dtype]["step"]
+        out = {"workload": f"{wl}: {N}x{H}x{W} {dtype} fwd+bwd per GPU", "batch": N, "ms_per_step": ms,
+               "Mpixel_per_s": cx.world * fz.P / (ms * 1e-3) / 1e6, "algorithmic_bytes_per_px": bpp,
+               "frac_of_hbm_roofline": fz.P * bpp / (ms * 1e-3) / 1e9 / peak, "timed_ms": total, "kernel_ms": kt}
+        if note:
+            out["note"] = note
+        fz.free()
+        return out
+    except Exception as exc:   # a sweep entry never takes the headline down
+        torch.cuda.empty_cache()
+        return {"workload": wl, "batch": N, "error": str(exc)[:200]}
 
 
 def main():
@@ -169,244 +595,98 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (c4: global batch); 0 = the workload's own")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-eager", action="store_true", help="skip timing the torch CUDA eager incumbent")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step (iters/s) measurement")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the compact lines of the other BASELINE configs")
+    ap.add_argument("--no-aux", action="store_true", help="skip the boundary-fusion / forward-warp side measurements")
     ap.add_argument("--flow-grad-only", action="store_true", help="sources are data: no d_src (128 B/px variant)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
-    import vlg_b200
-    from vlg_b200 import _cabi
-    from vlg_b200 import ops as vops
+    cx = Ctx()
+    vlg, dev, stream, dist = cx.vlg, cx.dev, cx.stream, cx.dist
+    wl = args.workload
+    N0, H, W, K, sigma, far, dtype = WORKLOADS[wl]
+    N = args.batch or N0
+    peak, peak_src = hbm_peak()
+    warmup = max(args.warmup, 3)
+    sampler = ClockSampler(cx.local_rank)
 
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=dev)
-
-    N, H, W, K, sigma, far, dtype = WORKLOADS[args.workload]
-    P = N * H * W
-    with_src = not args.flow_grad_only
-    lib = _cabi.load()
-    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
-
-    # two input sets, alternated, so no step re-reads lines its predecessor left in L2
-    sets = [make_inputs(N, H, W, K, sigma, far, dtype, dev, seed=1024 + 7 * rank + s) for s in range(2)]
-    cfg = vops.WarpLossConfig(w_tv=0.5)
-    prob = vops._problem(N, H, W, K, tdt, cfg)
-    ws = vops._workspace(prob, with_src, dev)
-    # same problem without the far path: vlg_warp_bwd_src then launches pass2_kernel ALONE, so that CUDA
-    # events bracket exactly one kernel (the far-path launches are idle for near flows and timed separately)
-    prob_p2 = vops._problem(N, H, W, K, tdt, vops.WarpLossConfig(w_tv=0.5, assume_near=True))
-    loss = torch.zeros(_cabi.LOSS_SLOTS, dtype=torch.float32, device=dev)
-    d_c = torch.empty(N, H, W, 2, dtype=torch.float32, device=dev)
-    d_a = vops.empty_nhwc((N, 3, H, W), tdt, dev) if with_src else None
-    d_b = vops.empty_nhwc((N, K, H, W), tdt, dev) if with_src else None
-    stream = torch.cuda.current_stream()
-    sp = C.c_void_p(stream.cuda_stream)
-    ptr = vops._ptr
-
-    def launch_fused(s, sp_):
-        vops.check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
-                                             ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(loss), ptr(d_c), ptr(d_a),
-                                             ptr(d_b), None, ptr(ws), ws.numel(), sp_))
-
-    def launch_pass1(s, sp_):
-        vops.check(lib.vlg_warp_loss_pass1(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
-                                           ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(loss), ptr(d_c), None, int(with_src),
-                                           ptr(ws), ws.numel(), sp_))
-
-    def launch_pass2(s, sp_):
-        if with_src:
-            vops.check(lib.vlg_warp_bwd_src(C.byref(prob), ptr(s["flow"]), ptr(d_a), ptr(d_b), ptr(ws), ws.numel(), sp_))
-
-    graphs = None
-    launches_per_step = None
-
-    def step(i, evs=None):
-        """One pass of the hot path.  The timed region uses the fused entry point (the last pass-1
-        CTA reduces the loss vector); with `evs` the same work is issued piecewise so that CUDA
-        events can bracket each kernel."""
-        s = sets[i & 1]
-        if evs is None and dist is not None:
-            # data parallel: the loss vector is complete after pass 1 (its last CTA reduces), so the path's only
-            # exchange -- one all-reduce of 8 floats -- is issued there and overlaps pass 2
-            if graphs is not None: graphs[i & 1][0].replay()
-            else: launch_pass1(s, sp)
-            work = dist.all_reduce(loss, async_op=True)
-            if graphs is not None: graphs[i & 1][1].replay()
-            else: launch_pass2(s, sp)
-            work.wait()
+    # ------------------------------------------------------------------ rollout workload (c4)
+    if wl == "c4":
+        if N % world:
+            raise SystemExit(f"global batch {N} is not divisible by {world} ranks")
+        ro = Rollout(cx, N // world)
+        for i in range(warmup):
+            ro.step(i)
+        cx.barrier()
+        n0 = vlg.launch_count()
+        ro.step(0)
+        launches_per_step = vlg.launch_count() - n0
+        if rank == 0:
+            sampler.start(); sampler.wait_first()
+        ms, r, total = cx.timed(ro.step, args.steps)
+        clocks = sampler.stop() if rank == 0 else None
+        e2e = ro.e2e(args.steps)
+        if rank != 0:
+            if dist is not None: dist.destroy_process_group()
             return
-        if evs is None and graphs is not None:
-            graphs[i & 1].replay()                  # the same launches, captured once per input set
-        elif evs is None:
-            launch_fused(s, sp)
-        else:
-            vops.check(lib.vlg_warp_loss_bwd_out(C.byref(prob), ptr(s["src_rgb"]), ptr(s["src_layout"]), ptr(s["flow"]),
-                                                 ptr(s["tgt_rgb"]), ptr(s["tgt_label"]), ptr(d_c), None, int(with_src),
-                                                 ptr(ws), ws.numel(), sp))
-            evs[1].record(stream)
-            vops.check(lib.vlg_reduce_partials(C.byref(prob), ptr(loss), ptr(ws), ws.numel(), sp))
-            evs[2].record(stream)
-            if with_src:
-                vops.check(lib.vlg_warp_bwd_src(C.byref(prob_p2), ptr(s["flow"]), ptr(d_a), ptr(d_b), ptr(ws), ws.numel(), sp))
-        if dist is not None:
-            dist.all_reduce(loss)          # the path's only exchange: one 8-float loss vector
-        if evs: evs[3].record(stream)
+        px_steps = world * ro.px_steps
+        achieved = ro.px_steps * ROLLOUT_BYTES_PER_PX / (ms * 1e-3) / 1e9
+        out = {"metric": "warp+loss fwd/bwd throughput", "value": px_steps / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world,
+               "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {**workload_config(wl, N, world, dtype), "per_gpu_batch": N // world,
+                          "unit_note": f"one step = one {ROLLOUT_STEPS}-frame rollout of the batch; Mpixel/s counts every warped frame",
+                          "replays_per_step": r, "timed_region_ms": total,
+                          "l2_policy": "inputs exceed the 126 MB L2 (%.0f MB of frames + flows per rollout)" % (ro.px_steps * 20 / 1e6)},
+               "roofline": {"bound": "hbm", "kernel": "warp_fwd_labels_kernel (x5, including the Python wrapper's allocations)",
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak_source": peak_src, "algorithmic_bytes_per_px": ROLLOUT_BYTES_PER_PX,
+                            "algorithmic_bytes": ro.px_steps * ROLLOUT_BYTES_PER_PX // ROLLOUT_STEPS, "kernel_ms": ms / ROLLOUT_STEPS},
+               "e2e": e2e, "gpu_launches": launches_per_step * args.steps * r, "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            v, t, sample = cpu_oracle_run(wl, N, 3, 1)
+            out["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+        print(json.dumps(out))
+        if dist is not None: dist.destroy_process_group()
+        return
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    # CUDA graph of the step's launches (memset + count + pass 1 + far path + pass 2), one per input set
-    if not args.no_graph:
-        try:
-            n_before = vlg_b200.launch_count()
-            gs = []
-            for k in range(2):
-                if dist is None:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        launch_fused(sets[k], C.c_void_p(torch.cuda.current_stream().cuda_stream))
-                    gs.append(g)
-                else:   # two graphs per input set: the all-reduce is issued between them
-                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1):
-                        launch_pass1(sets[k], C.c_void_p(torch.cuda.current_stream().cuda_stream))
-                    with torch.cuda.graph(g2):
-                        launch_pass2(sets[k], C.c_void_p(torch.cuda.current_stream().cuda_stream))
-                    gs.append((g1, g2))
-            launches_per_step = (vlg_b200.launch_count() - n_before) // 2
-            graphs = gs
-            for i in range(4):
-                step(i)
-            barrier()
-        except Exception as exc:   # capture unsupported: plain launches
-            print(f"[bench] CUDA graph capture failed ({exc}); using plain launches", file=sys.stderr)
-            graphs = None
+    # ------------------------------------------------------------------ fused warp + loss workloads
+    with_src = not args.flow_grad_only
+    fz = Fused(cx, wl, N, with_src=with_src, use_graph=not args.no_graph)
+    for i in range(warmup):
+        fz.step(i)
+    cx.barrier()
 
     # ---- timed region 1: device-resident throughput (`value`) ----
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = vlg_b200.launch_count()
-    barrier()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    e1.record(stream)
-    barrier()
-    launches = vlg_b200.launch_count() - n0
-    if graphs is not None:
-        launches = launches_per_step * args.steps   # replayed from the graph: the host counter does not move
-    ms_total = e0.elapsed_time(e1)
-    t_step = torch.tensor([ms_total / args.steps], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
-    ms_per_step = t_step.item()
+        sampler.start(); sampler.wait_first()
+    ms_per_step, replays, timed_ms = cx.timed(fz.step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    launches = fz.count_launches(args.steps * replays)
 
-    # ---- per-kernel timing (same stream, CUDA events between the launches) ----
-    reps = min(args.steps, 20)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
-    barrier()
-    for i in range(reps):
-        evs[i][0].record(stream)
-        step(i, evs[i])
-    barrier()
-    k1 = sorted(e[0].elapsed_time(e[1]) for e in evs)[reps // 2]   # pass-1 stage: memset + count_valid + rgb strip + layout tile
-    k2 = sorted(e[2].elapsed_time(e[3]) for e in evs)[reps // 2]   # pass2_kernel alone (+ the all-reduce when world > 1)
-    kr = sorted(e[1].elapsed_time(e[2]) for e in evs)[reps // 2]
-
-    # ---- per-kernel device times of the fused step (CUPTI through torch.profiler; informational) ----
-    kernels_us = None
-    if rank == 0:
-        try:
-            from torch.profiler import profile, ProfilerActivity
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                for i in range(10):
-                    launch_fused(sets[i & 1], sp)
-                torch.cuda.synchronize()
-            kernels_us = {e.key.split("(")[0].replace("void ", "").replace("vlg::", ""): round(e.device_time_total / 10, 2)
-                          for e in prof.key_averages() if e.device_time_total > 0}
-        except Exception as exc:   # profiler unavailable: the event timings above stand on their own
-            kernels_us = {"unavailable": str(exc)}
+    # ---- per-kernel device times inside the direct launch sequence (CUDA events on the launch stream) ----
+    kt = fz.kernel_times(reps=20)
+    kernels_us = fz.cupti_table() if rank == 0 else None
 
     # ---- timed region 2: end to end through the public module API from pinned host memory ----
-    # The source layout travels as the class-id map the reference's dataset hands out (float32 [N,1,H,W],
-    # src/folder.py:97-99) and is one-hot encoded on the device like src/models/net_utils.py:14-24
-    # (`vlg_one_hot`): 4 bytes per pixel over PCIe instead of 4*K.
-    host = {k: v.cpu().pin_memory() for k, v in sets[0].items() if k != "src_layout"}
-    host["src_seg"] = sets[0]["src_layout"].argmax(1, keepdim=True).float().cpu().pin_memory()
-    crit = vlg_b200.WarpLoss(weights=(40.0, 20.0, 10.0, 0.5))
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-
-    # Double-buffered: while step i computes, the inputs of step i+1 travel on a copy stream into the other
-    # device buffer set (what a DataLoader prefetcher does).  Every step still uploads one full input set
-    # and reads its result back; the timed region holds exactly n_e2e uploads, n_e2e steps, n_e2e reads.
-    copy_stream = torch.cuda.Stream(device=dev)
-    dbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
-    for b_ in dbuf:   # keep the NHWC storage of the image tensors
-        for k in ("src_rgb", "tgt_rgb"):
-            b_[k] = torch.empty_strided(host[k].shape, host[k].stride(), dtype=host[k].dtype, device=dev)
-    up_done = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def upload(j):
-        with torch.cuda.stream(copy_stream):
-            for k, v in host.items():
-                dbuf[j][k].copy_(v, non_blocking=True)
-            up_done[j].record(copy_stream)
-
-    def e2e_step(i):
-        j = i & 1
-        upload(j ^ 1)                      # inputs of the NEXT step (its buffer was released by the previous read-back)
-        stream.wait_event(up_done[j])
-        cur = dbuf[j]
-        a = cur["src_rgb"].detach().requires_grad_(with_src)
-        b = vlg_b200.one_hot_layout(cur["src_seg"], K, tdt).requires_grad_(with_src)
-        f = cur["flow"].detach().requires_grad_(True)
-        total = crit(a, b, f, cur["tgt_rgb"], cur["tgt_label"])
-        total.backward()
-        return crit.last_terms.cpu()       # device -> host read of the step's result (synchronises)
-
-    upload(0)
-    for i in range(4):
-        e2e_step(i)
-    barrier()
-    n_e2e = max(4, min(args.steps, 10)) & ~1
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    for i in range(n_e2e):
-        e2e_step(i)
-    e3.record(stream)
-    barrier()
-    t_e2e = torch.tensor([e2.elapsed_time(e3) / n_e2e], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e = e2e_fused(cx, fz, args.steps)
 
     # ---- incumbent on the same GPU: the oracle composition run by torch CUDA eager (ATen kernels) ----
     eager = None
-    if rank == 0 and dtype == "f32" and not args.no_eager:
+    if rank == 0 and dtype == "f32" and not args.no_eager and fz.P <= 4 * 1024 * 1024:
         from oracle import torch_oracle as TO
-        s0 = sets[0]
+        s0 = fz.sets[0]
+
         def eager_step():
             a = s0["src_rgb"].detach().requires_grad_(with_src)
             b = s0["src_layout"].detach().requires_grad_(with_src)
@@ -423,28 +703,16 @@ def main():
         g1.record(stream)
         torch.cuda.synchronize()
         ms_eager = g0.elapsed_time(g1) / 5
-        eager = {"ms_per_step": ms_eager, "value": P / (ms_eager * 1e-3) / 1e6, "unit": "Mpixel/s",
+        eager = {"ms_per_step": ms_eager, "value": fz.P / (ms_eager * 1e-3) / 1e6, "unit": "Mpixel/s",
                  "what": "oracle composition (F.grid_sample + losses + autograd) in torch CUDA eager, same inputs, checker only"}
 
-    # ---- boundary fusion: renorm + flip + NCHW->NHWC of rgb frames, one pass, HBM-bound ----
+    P = fz.P
+    graph_used = fz.graphs is not None
+    fz.free()
+
+    # ---- side measurements on rank 0: boundary fusion, ingest, forward warp (HBM-bound passes) ----
     aux = None
-    if rank == 0:
-        fr = torch.rand(8, 3, 1024, 2048, device=dev)          # 403 MB read+written per call: larger than the L2
-        for _ in range(3):
-            vlg_b200.prepare_frames(fr, flip=True)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        for _ in range(10):
-            vlg_b200.prepare_frames(fr, flip=True)
-        a1.record(stream)
-        torch.cuda.synchronize()
-        ms_fa = a0.elapsed_time(a1) / 10
-        gbs = fr.numel() * 4 * 2 / (ms_fa * 1e-3) / 1e9
-        aux = {"frame_affine": {"what": "vlg_frame_affine 8x3x1024x2048 fp32 NCHW -> normalised, flipped NHWC (24 B/px algorithmic; "
-                                        "includes the output allocation of the Python wrapper)",
-                                "ms": ms_fa, "achieved_GBs": gbs}}
-        del fr
-        # ---- rollout (BASELINE config 4): 5 autoregressive steps at 512x1024 with LABEL layout sources ----
+    if rank == 0 and not args.no_aux:
         def timed(fn, reps):
             for _ in range(2):
                 fn()
@@ -455,30 +723,56 @@ def main():
             t1_.record(stream)
             torch.cuda.synchronize()
             return t0_.elapsed_time(t1_) / reps
-        rn, rh, rw = 4, 512, 1024                                # 32 / 8 GPUs per rank
-        rd = make_inputs(rn, rh, rw, K, sigma, 0.0, "f32", dev, seed=77)
-        rlab = rd["src_layout"].argmax(1)
-        rflows = [make_inputs(rn, rh, rw, K, sigma, 0.0, "f32", dev, seed=78 + t)["flow"] for t in range(5)]
-        ms_ro = timed(lambda: vlg_b200.rollout(rd["src_rgb"], rlab, lambda t, im, lb: rflows[t], steps=5), 5)
-        ro_px = rn * rh * rw * 5
-        # per step and pixel: coords 8 + rgb 12 + label 8 read, rgb 12 + label 8 written = 48 B
-        aux["rollout"] = {"what": "vlg_warp_fwd_labels x5 (4x512x1024 per GPU, label sources fed back: 48 B/px algorithmic "
-                                  "against 200 B/px with dense one-hot layouts); includes the Python wrapper's allocations",
-                          "ms": ms_ro, "Mpixel_steps_per_s": ro_px / (ms_ro * 1e-3) / 1e6,
-                          "achieved_GBs": ro_px * 48 / (ms_ro * 1e-3) / 1e9}
-        # ---- validation forward (BASELINE config 3 shape, one image set that exceeds the L2): warp + argmax, outputs materialised ----
+        fr = torch.rand(8, 3, 1024, 2048, device=dev)          # 403 MB read+written per call: larger than the L2
+        ms_fa = timed(lambda: vlg.prepare_frames(fr, flip=True), 10)
+        aux = {"frame_affine": {"what": "vlg_frame_affine 8x3x1024x2048 fp32 NCHW -> normalised, flipped NHWC (24 B/px algorithmic; "
+                                        "includes the output allocation of the Python wrapper)",
+                                "ms": ms_fa, "achieved_GBs": fr.numel() * 4 * 2 / (ms_fa * 1e-3) / 1e9}}
+        del fr
+        u8 = torch.randint(0, 256, (8, 1024, 2048, 3), dtype=torch.uint8, device=dev)
+        sg = torch.randint(0, K, (8, 1024, 2048), dtype=torch.uint8, device=dev)
+        ms_in = timed(lambda: vlg.ingest(u8, sg, n_classes=K, want_label=True, want_one_hot=True), 5)
+        in_px = 8 * 1024 * 2048
+        aux["ingest"] = {"what": "vlg_ingest 8x1024x2048: uint8 frame + class map -> normalised fp32 NHWC frame, int64 label, one-hot "
+                                 "layout (4 B/px read, 12 + 8 + 80 written; includes the Python wrapper's allocations)", "ms": ms_in,
+                         "achieved_GBs": in_px * 104 / (ms_in * 1e-3) / 1e9}
+        del u8, sg
         vn, vh, vw = 2, 1024, 2048
-        vd = make_inputs(vn, vh, vw, K, sigma, 0.0, dtype, dev, seed=79)
-        ms_fw = timed(lambda: vlg_b200.warp(vd["src_rgb"], vd["src_layout"], vd["flow"]), 5)
+        vd = make_inputs(vn, vh, vw, K, 4.0, 0.0, dtype, dev, seed=79)
+        ms_fw = timed(lambda: vlg.warp(vd["src_rgb"], vd["src_layout"], vd["flow"]), 5)
         fw_bpp = 200 if dtype == "f32" else 108
         aux["warp_fwd"] = {"what": f"vlg_warp_fwd {vn}x{vh}x{vw} {dtype}: warped rgb + layout + argmax written ({fw_bpp} B/px algorithmic)",
                            "ms": ms_fw, "Mpixel_per_s": vn * vh * vw / (ms_fw * 1e-3) / 1e6,
                            "achieved_GBs": vn * vh * vw * fw_bpp / (ms_fw * 1e-3) / 1e9}
-        del rd, rflows, vd
+        del vd
+        for k_ in aux:
+            aux[k_]["frac_of_hbm_peak"] = aux[k_]["achieved_GBs"] / peak
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, compact (every rank takes part: weak scaling / per-rank rollout shards) ----
+    sweep = None
+    if not args.no_sweep and wl == "c2":
+        sweep = {}
+        sweep["c3"] = sweep_entry(cx, "c3", WORKLOADS["c3"][0], 5, peak)
+        for B in (1, 4, 16, 64):
+            sweep[f"c5_b{B}"] = sweep_entry(cx, "c5", B, 5, peak)
+        try:
+            n_rank = WORKLOADS["c4"][0] // 8                      # the dp8 shard of BASELINE config 4
+            ro = Rollout(cx, n_rank)
+            ms_ro, r_, tot_ = cx.timed(ro.step, 3, min_ms=120.0)
+            sweep["c4_dp8_shard"] = {"workload": f"c4: {ROLLOUT_STEPS}-step rollout, {n_rank}x512x1024 per GPU (global batch 32 over 8 GPUs)",
+                                     "ms_per_rollout": ms_ro, "Mpixel_steps_per_s": world * ro.px_steps / (ms_ro * 1e-3) / 1e6,
+                                     "algorithmic_bytes_per_px": ROLLOUT_BYTES_PER_PX,
+                                     "frac_of_hbm_roofline": ro.px_steps * ROLLOUT_BYTES_PER_PX / (ms_ro * 1e-3) / 1e9 / peak,
+                                     "note": "includes the Python wrapper's per-step allocations"}
+            del ro
+        except Exception as exc:
+            sweep["c4_dp8_shard"] = {"error": str(exc)[:200]}
+        torch.cuda.empty_cache()
 
     # ---- training step: torch flow producer -> fused op -> DDP -> Adam, iters/s ----
     train = None
-    if args.workload == "c2" and not args.no_train:
+    if wl == "c2" and not args.no_train:
         from train import run_training
         train, _ = run_training(steps=max(3, min(args.steps, 10)), warmup=2, batch=N, height=H, width=W, classes=K)
 
@@ -487,65 +781,49 @@ def main():
             dist.destroy_process_group()
         return
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
     bpp = BYTES_PER_PX[dtype]
     step_bytes = bpp["step"] if with_src else bpp["pass1"]
     value = world * P / (ms_per_step * 1e-3) / 1e6
-    # dominant single kernel: pass2_rec_kernel (deterministic source gradient from pass 1's tap records); without source gradients the
-    # pass-1 stage (rgb strip + layout tile kernels, not separately callable) is reported instead
-    dom_name, dom_ms, dom_bytes = ("pass2_rec_kernel", k2, bpp["pass2"]) if with_src else ("pass-1 stage (rgb_strip_kernel + lay_tile_kernel)", k1, bpp["pass1"])
-    achieved = P * dom_bytes / (dom_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full`
-    # capture of this same workload (profiles/r01_ncu_traffic.json); null for other workloads
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if args.workload == "c2" and with_src and os.path.exists(tpath):
-        k = json.load(open(tpath))["kernels"].get(dom_name)
-        if k:
-            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
+    # the longest kernel of the step, timed by CUDA events on its launch stream inside the direct launch sequence
+    kb = {"rgb_strip_kernel": bpp["rgb_strip"], "lay_tile_kernel": bpp["lay_tile"], "pass2_rec_kernel": bpp["pass2"]}
+    live = {k: v for k, v in kt.items() if k in kb and v > 0}
+    dom = max(live, key=live.get)
+    dom_ms = live[dom]
+    achieved = P * kb[dom] / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom) if wl == "c2" and with_src else (None, None)
     out = {
         "metric": "warp+loss fwd/bwd throughput", "value": value, "unit": "Mpixel/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {N}x{H}x{W} K={K} {dtype} warp+loss fwd+bwd per GPU"
-                               + ("" if with_src else " (flow-grad only)"),
-                   "per_gpu_pixels": P, "grads": "flow,src_rgb,src_layout" if with_src else "flow",
+        "config": {**workload_config(wl, N, world, dtype, with_src),
                    "l2_policy": "inputs (%.0f MB/step) exceed the 126 MB L2; two input sets alternate" % (P * 120 / 1e6),
-                   "parallelism": f"dp{world}", "launch": "cuda graph replay" if graphs is not None else "direct launches",
+                   "launch": "cuda graph replay" if graph_used else "direct launches",
+                   "replays_per_step": replays, "timed_region_ms": timed_ms,
+                   "timing_note": f"the timed region is {args.steps} step groups of {replays} passes each (>= {MIN_TIMED_MS:.0f} ms); "
+                                  "ms_per_step is per single pass",
                    "exchange": ("one NCCL all-reduce of the 8-float loss vector per step, issued after pass 1 and overlapped with pass 2"
                                 if world > 1 else "none (single GPU)")},
-        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes": P * dom_bytes,
-                     "algorithmic_bytes_per_px": dom_bytes, "kernel_ms": dom_ms},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes": P * kb[dom], "algorithmic_bytes_per_px": kb[dom], "kernel_ms": dom_ms},
+        "roofline_kernels": {k: {"kernel_ms": v, "algorithmic_bytes_per_px": kb[k], "achieved": P * kb[k] / (v * 1e-3) / 1e9,
+                                 "frac": P * kb[k] / (v * 1e-3) / 1e9 / peak} for k, v in live.items()},
         "roofline_step": {"algorithmic_bytes_per_px": step_bytes,
                           "achieved": P * step_bytes / (ms_per_step * 1e-3) / 1e9,
                           "frac": P * step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                          "kernel_ms": {"pass1_stage(memset+count+rgb_strip+lay_tile)": k1, "reduce(standalone)": kr, "pass2_rec_kernel": k2},
+                          "span_first_to_last_kernel_ms": kt["span_first_to_last"],
                           "kernels_us_cupti": kernels_us},
-        "e2e": {"value": world * P / (t_e2e.item() * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": _cabi.LOSS_SLOTS * 4, "ms_per_step": t_e2e.item(),
-                "inputs": "pinned host: src_rgb, tgt_rgb, flow (fp32), tgt_label (int64), source layout as the dataset's float32 "
-                          "class-id map (src/folder.py:97-99), one-hot encoded on the device (src/models/net_utils.py:14-24); "
-                          "double-buffered: step i+1 uploads on a copy stream while step i computes"},
+        "e2e": e2e,
         "gpu_launches": launches,
         "clocks": clocks,
+        "sweep": sweep,
         "train": train,
         "torch_cuda_eager": eager,
         "aux": aux,
     }
-    if aux:
-        for k_ in aux:
-            aux[k_]["frac_of_hbm_peak"] = aux[k_]["achieved_GBs"] / peak
     if world == 1 and not args.no_cpu_baseline:
-        n_sample = min(N, 4)
-        v, t = cpu_oracle_throughput(N, H, W, K, sigma, far, n_sample, iters=5)
-        out["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"{n_sample}x{H}x{W} slice of the batch, torch CPU oracle port fwd+bwd, median of 5 ({t*1e3:.0f} ms/iter)"}
+        v, t, sample = cpu_oracle_run(wl, N, 5, 1)
+        out["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -251,6 +251,15 @@ int vlg_read_status(void *workspace, size_t workspace_bytes, uint32_t *host_stat
 /* Number of kernels the library has launched in this process (for bench.py's gpu_launches). */
 int64_t vlg_launch_count(void);
 
+/* Measurement aid (bench.py's per-kernel roofline; no reference counterpart).  While armed on the calling thread
+ * (on != 0), vlg_warp_loss_* / vlg_warp_bwd_src record CUDA events on their launch stream right before and after the
+ * three main kernels of the step.  vlg_timeline_read waits for the last recorded event and returns device times in
+ * milliseconds of the most recent armed call sequence: ms4[0] rgb_strip_kernel, ms4[1] lay_tile_kernel, ms4[2] the
+ * pass-2 gather kernel, ms4[3] first event to last event; -1 where a kernel did not run.  Do not arm while the
+ * stream is being captured into a CUDA graph. */
+int vlg_timeline_arm(int on);
+int vlg_timeline_read(float *ms4);
+
 #ifdef __cplusplus
 }
 #endif

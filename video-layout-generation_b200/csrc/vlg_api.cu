@@ -46,6 +46,23 @@ static int check_launch(const char *what) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- kernel timeline (measurement aid behind vlg_timeline_arm / vlg_timeline_read) ----
+// While armed on the calling thread, the fused entry points record CUDA events on their launch stream right before
+// and after the three main kernels, so that a benchmark can time each kernel inside the real launch sequence.
+enum { kTlRgb0, kTlRgb1, kTlLay0, kTlLay1, kTlP2a, kTlP2b, kTlCount };
+struct Timeline {
+    bool armed = false;
+    int dev = -1;
+    unsigned seen = 0;
+    cudaEvent_t ev[kTlCount] = {};
+};
+static thread_local Timeline g_tl;
+static void tl_mark(int i, cudaStream_t st) {
+    if (!g_tl.armed) return;
+    if (cudaEventRecord(g_tl.ev[i], st) == cudaSuccess) g_tl.seen |= 1u << i;
+    else (void)cudaGetLastError();
+}
+
 // ---- per-device launch state ----
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy-derived grid sizes belong to a DEVICE, not to the
 // process: a process that drives several GPUs (nn.DataParallel at src/val.py:131, one thread per device, ...) must
@@ -543,8 +560,10 @@ static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_p
             constexpr size_t smem_rec = sizeof(Pass2RecSmem<K>);
             static PerDevice rec_attr;  // per instantiation
             if (int rc = ensure_smem(rec_attr, pass2_rec_kernel<T, K>, smem_rec, "pass2_rec")) return rc;
+            tl_mark(kTlP2a, st);
             pass2_rec_kernel<T, K><<<dim3((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N), kThreads, smem_rec, st>>>(
                 pp, lay_map, rgb_map, frac_map, code_map);
+            tl_mark(kTlP2b, st);
             return check_launch("pass2_rec_kernel");
         }
     }
@@ -557,7 +576,9 @@ static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_p
     pp.use_tma = (pp.d_src_lay && pp.d_out_lay && !(prob->flags & VLG_FLAG_NO_TMA) &&
                   make_layout_map(prob, pp.d_out_lay, &dout_map, kQW, kQH, true)) ? 1 : 0;
     if (!pp.use_tma) memset(&dout_map, 0, sizeof(dout_map));
+    tl_mark(kTlP2a, st);
     pass2_kernel<T, K><<<dim3((unsigned)pp.tiles_x, (unsigned)pp.tiles_y, (unsigned)pp.N), kThreads, smem, st>>>(pp, dout_map);
+    tl_mark(kTlP2b, st);
     return check_launch("pass2_kernel");
 }
 
@@ -756,7 +777,9 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
         rp.pitch = (int)L.pitch;
         rp.partials = (float *)(ws + L.partials_rgb);
         rp.hdr = hdr;
+        tl_mark(kTlRgb0, st);
         int rc0 = prob->dtype == VLG_F32 ? launch_rgb<float>(rp, need_grad, st) : launch_rgb<__nv_bfloat16>(rp, need_grad, st);
+        tl_mark(kTlRgb1, st);
         if (rc0) return rc0;
         pp.src_rgb = nullptr; pp.tgt_rgb = nullptr; pp.d_out_rgb = nullptr;
         pp.accum_dcoords = 1;
@@ -787,7 +810,9 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             lp.partials = (float *)(ws + L.partials_lay);
             lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
             lp.red = pp.red; lp.hdr = hdr;
+            tl_mark(kTlLay0, st);
             rc = dispatch_laytile(prob, lp, row_map, px8, need_grad, st);
+            tl_mark(kTlLay1, st);
             if (rc) return rc;
             lay_done = true;
         }
@@ -919,6 +944,43 @@ int64_t vlg_launch_count(void) { return g_launches.load(); }
 size_t vlg_workspace_bytes(const vlg_problem_t *prob, int with_src_grad) {
     if (check_problem(prob)) return 0;
     return ws_layout(prob, with_src_grad).total;
+}
+
+int vlg_timeline_arm(int on) {
+    int dev = -1;
+    if (int rc = current_device(&dev)) return rc;
+    if (on && g_tl.dev != dev) {
+        for (int i = 0; i < kTlCount; ++i)
+            if (cudaEventCreate(&g_tl.ev[i]) != cudaSuccess) return fail(VLG_ERR_CUDA, "cudaEventCreate failed");
+        g_tl.dev = dev;
+    }
+    g_tl.armed = on != 0;
+    if (on) g_tl.seen = 0;
+    return VLG_OK;
+}
+
+int vlg_timeline_read(float *ms4) {
+    if (!ms4) return fail(VLG_ERR_ARG, "ms4 is NULL");
+    if (g_tl.dev < 0) return fail(VLG_ERR_ARG, "vlg_timeline_arm was never called on this thread");
+    const int pairs[3][2] = {{kTlRgb0, kTlRgb1}, {kTlLay0, kTlLay1}, {kTlP2a, kTlP2b}};
+    int first = -1, last = -1;
+    for (int i = 0; i < kTlCount; ++i)
+        if (g_tl.seen & (1u << i)) { if (first < 0) first = i; last = i; }
+    if (last >= 0 && cudaEventSynchronize(g_tl.ev[last]) != cudaSuccess) return fail(VLG_ERR_CUDA, "timeline: event synchronize failed");
+    for (int k = 0; k < 3; ++k) {
+        ms4[k] = -1.0f;
+        const unsigned need = (1u << pairs[k][0]) | (1u << pairs[k][1]);
+        if ((g_tl.seen & need) == need && cudaEventElapsedTime(&ms4[k], g_tl.ev[pairs[k][0]], g_tl.ev[pairs[k][1]]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ms4[k] = -1.0f;
+        }
+    }
+    ms4[3] = -1.0f;
+    if (first >= 0 && last > first && cudaEventElapsedTime(&ms4[3], g_tl.ev[first], g_tl.ev[last]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        ms4[3] = -1.0f;
+    }
+    return VLG_OK;
 }
 
 int vlg_warp_fwd(const vlg_problem_t *prob, const void *src_rgb, const void *src_layout, const float *coords,
