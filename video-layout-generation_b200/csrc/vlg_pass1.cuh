@@ -126,11 +126,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // suspend-time hint: the warp sleeps in hardware
+        "@p bra WAIT_DONE;\n"                                             // instead of burning issue slots on a spin loop
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
-        "}\n" ::"r"(a), "r"(parity)
+        "}\n" ::"r"(a), "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {

@@ -261,34 +261,11 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_kernel(const Pass2Params p,
 //   fraction window   [kQH][kQW2]        float2
 //   code window       [kQH][kQW2]        uint32 -- out-of-image cells arrive as 0 = "no contribution"
 // the first anchored at (tx0 - kRMax, ty0 - kRMax), the narrow-pixel ones at (tx0 - kQX2, ty0 - kRMax): a TMA box must
-// start on a 16-byte boundary, i.e. on a column that is a multiple of 4 for the 12-, 8- and 4-byte pixels.
-//
-// Cell-ordered gather.  A source pixel s receives from the output pixels whose NW tap cell is one of the four
-// cells s - (a, b), a, b in {0, 1}.  The first version of this kernel found them by scanning the (2r+1)^2
-// candidates around s and ran its ~40-instruction hit body once per DISTINCT hit offset among the warp's
-// pixels: 17 bodies per warp for the benchmark flow (zero-mean, +-1 px: floor() takes two values per axis, two
-// taps per axis -> up to 16 offsets), a quarter of the lanes active in each -- 77 % of the kernel's
-// instructions.  Now the candidates register themselves in a per-CTA INVERSE MAP, cell -> contributors, and the
-// gather walks the four cells in a fixed order: one body per cell with (almost) all lanes active.
-//   * The map holds up to four contributors per cell, one byte each (the contributor's position relative to the
-//     cell, 6 bits), four bytes = one word per cell.  It is built with plain shared-memory byte stores in rounds
-//     separated by CTA barriers: in round k every candidate that has no slot yet stores its code in byte k of its
-//     cell (some writer wins), and after the barrier the winner recognises itself.  Which candidate wins a byte
-//     is a race, but the SET of bytes is not (for <= 4 contributors it is all of them), and the gather sorts the
-//     bytes by value (= raster order of the contributors): the summation order is a function of the data alone
-//     -> bitwise reproducible.  Rounds stop as soon as every candidate has a slot (benchmark flow: 68 % of the
-//     cells hold one contributor, 14 % two, 1.1 % three, 0.15 % four).
-//   * Cells with more than four contributors (flow that compresses five output pixels into one source cell) are
-//     marked, and the source pixels around them go through the scan of the first version (every candidate of
-//     the window, fixed order).
-// Summation order: the smallest contributor of cells (0,0), (1,0), (0,1), (1,1), then the others cell by cell.
+// start on a 16-byte boundary, i.e. on a column that is a multiple of 4 for the 12-, 8- and 4-byte pixels.  The scan / hit loop is the same as pass2_kernel's, in the
+// same order, so both kernels produce bit-identical gradients.
 constexpr int kQW2 = 40;   // window width of the 12-, 8- and 4-byte-pixel arrays: rows of 480 / 320 / 160 bytes
 constexpr int kQX2 = 4;    // their left margin (>= kRMax, multiple of 4; kTW is a multiple of 4 too)
 static_assert(kQX2 >= kRMax && kQX2 % 4 == 0 && kTW % 4 == 0 && kQX2 + kTW + kRMax <= kQW2, "narrow-pixel window geometry");
-constexpr int kCW = kTW + 1, kCH = kTH + 1, kCN = kCW * kCH;   // cells that can feed the tile: NW corner in [-1, kTW) x [-1, kTH)
-constexpr uint32_t kSlotEmpty = 0xFFu, kSlotOverflow = 0xFEu;
-constexpr int kSlots = 4;
-static_assert(kRMax == 3, "the 6-bit contributor code holds x - x0, y - y0 in [-2, 3]");
 
 template <int K>
 struct Pass2RecSmem {
@@ -297,7 +274,6 @@ struct Pass2RecSmem {
     alignas(128) float2 frac[kQH * kQW2];
     alignas(128) uint32_t code[kQH * kQW2];
     alignas(8) uint64_t bar;
-    uint32_t slot[kCN];        // inverse map: four contributor codes per cell (kSlotEmpty = none)
 };
 
 template <typename T, int K>
@@ -330,134 +306,53 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Param
         if (want_lay) tma_load_4d(sm.lay, &lay_map, &sm.bar, 0, tx0 - kRMax, ty0 - kRMax, n);
         if (want_rgb) tma_load_3d(sm.rgb, &rgb_map, &sm.bar, (tx0 - kQX2) * 3, ty0 - kRMax, n);
     }
-    // empty inverse map (overlaps the flight of the windows)
-    for (int i = tid; i < kCN; i += kThreads) sm.slot[i] = 0xFFFFFFFFu;
     const uint32_t tile_far = p.far_acc ? __ldg(p.tile_flags + bt) : 0u;   // consumed at the very end: issue early
-    __syncthreads();          // the barrier object is initialised, the map is empty
+    const int r = near_radius(p, n, blockIdx.y, blockIdx.x);
+    __syncthreads();          // the barrier object is initialised
     mbar_wait(&sm.bar, 0);    // the four windows have landed
 
-    // ---- inverse map: every candidate output pixel of the window registers in the cell of its NW tap ----
-    constexpr int kCand = kQH * kQW2, kCIt = (kCand + kThreads - 1) / kThreads;
-    uint8_t *slot8 = reinterpret_cast<uint8_t *>(sm.slot);
-    int ci[kCIt];             // byte offset of the candidate's cell word, -1: no slot wanted (any more)
-    uint32_t rel[kCIt];
-    bool wrote = false;
-#pragma unroll
-    for (int it = 0; it < kCIt; ++it) {
-        const int q = tid + it * kThreads;
-        ci[it] = -1; rel[it] = 0u;
-        if (q < kCand) {
-            const uint32_t code = sm.code[q];
-            const int row = (q * 1639) >> 16, col = q - row * kQW2;          // q / 40 for q < 1311
-            const int x0r = (int)(code & 0xFFFFu) - 8, y0r = (int)(code >> 16) - 8;   // x0 - x, y0 - y in [-3, 2]
-            const int cx = col - kQX2 + x0r + 1, cy = row - kRMax + y0r + 1;  // cell relative to the tile, biased by 1
-            if (code != 0u && (unsigned)cx < (unsigned)kCW && (unsigned)cy < (unsigned)kCH) {
-                ci[it] = (cy * kCW + cx) * kSlots;
-                rel[it] = (uint32_t)(2 - x0r) | ((uint32_t)(2 - y0r) << 3);   // (x - x0 + 2) | (y - y0 + 2) << 3, raster order
-                slot8[ci[it]] = (uint8_t)rel[it];
-                wrote = true;
-            }
-        }
-    }
-    static_assert(kCand < 1311, "q / 40 by multiply-shift");
-    // round k: the barrier publishes byte k; a candidate that does not find itself there tries byte k + 1
-#pragma unroll 1
-    for (int k = 0; k < kSlots; ++k) {
-        if (!__syncthreads_or(wrote)) break;
-        wrote = false;
-#pragma unroll
-        for (int it = 0; it < kCIt; ++it) {
-            if (ci[it] < 0) continue;
-            if (slot8[ci[it] + k] == rel[it]) { ci[it] = -1; continue; }
-            slot8[ci[it] + (k + 1 < kSlots ? k + 1 : kSlots - 1)] = (uint8_t)(k + 1 < kSlots ? rel[it] : kSlotOverflow);
-            wrote = true;
-        }
-        if (k == kSlots - 1) __syncthreads();     // overflow marks (if any) are visible to the gather
-    }
-
-    // ---- one thread per source pixel (warp = tile row): fixed-order gather over the four cells ----
-    const int tx = lane, ty = wid;
-    static_assert(kTW == 32 && kTH * 32 == kThreads, "row mapping");
+    // ---- one thread per source pixel: fixed-order gather ----
+    // A warp owns a compact 8 x 4 PATCH of the tile, not a 32-pixel row: the hit body below runs once per distinct
+    // hit offset among the warp's pixels, and the flow varies less across a patch than along a row (fewer, fuller
+    // bodies).  A quarter-warp is still 8 consecutive pixels of one row, so the 80-byte-pixel fetches stay
+    // conflict-free.
+    const int tx = (wid & 3) * 8 + (lane & 7), ty = (wid >> 2) * 4 + (lane >> 3);
+    static_assert(kTW == 32 && kTH == 8, "patch mapping");
     const int sy = ty0 + ty, sx = tx0 + tx;
     const bool live = sy < H && sx < W;
     float acc_l[K], acc_r[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < K; ++k) acc_l[k] = 0.f;
-    // contribution of the candidate at window cell (row, col) [narrow-pixel windows] through its tap (a, b)
-    auto hit = [&](int row, int col, bool a, bool b) {
-        const int cell = row * kQW2 + col;
-        const float2 f = sm.frac[cell];
-        // east/south = frac, west/north = 1 - frac: bit-identical to the forward's (x0 + 1) - ix for every
-        // in-image tap (both are exact for x0 >= 1, and the same expression for x0 == 0)
-        const float wx = a ? f.x : __fsub_rn(1.0f, f.x);
-        const float wy = b ? f.y : __fsub_rn(1.0f, f.y);
-        const float w = __fmul_rn(wx, wy);
-        if (want_lay) {
-            float v[K];
-            load_px_smem<float, K>(sm.lay + (size_t)(row * kQW + col - (kQX2 - kRMax)) * K, v);
-            fma2_bcast<K>(acc_l, v, w);
-        }
-        if (want_rgb) {
+    for (int dy = live ? -r : r + 1; dy <= r; ++dy) {
+        // candidate output pixel (sx + ddx, sy + dy), ddx = j - r, sits at window cell (ty + kRMax + dy, tx + kQX2 + ddx).
+        // With its record code = (x0 - x + 8) | (y0 - y + 8) << 16,
+        //   e = ((8 - ddx) | (8 - dy) << 16) - code = (sx - x0) | (sy - y0) << 16:
+        // a hit iff both differences are 0 (west / north tap) or 1 (east / south tap); any other difference
+        // (incl. borrows, and code 0) leaves a bit outside {0, 16}.
+        const int crow = (ty + kRMax + dy) * kQW2 + tx + kQX2 - r;
+        const uint32_t c0 = (uint32_t)(8 + r) | ((uint32_t)(8 - dy) << 16);
+        uint32_t ev[2 * kRMax + 1];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc_r[c] = fmaf(w, sm.rgb[cell * 3 + c], acc_r[c]);
-        }
-    };
-    if (live) {
-        const int cb = (ty + 1) * kCW + (tx + 1);
-        uint32_t lo[4];            // smallest contributor of each cell (kSlotEmpty: none)
-        uint64_t pend = 0ull;      // the other contributors, in summation order: (code | cell << 6), one byte each
-        int np = 0;
-        bool slow = false;
-        auto push = [&](uint32_t e, int t) {
-            if (np == 8) slow = true;
-            else { pend |= (uint64_t)(e | ((uint32_t)t << 6)) << (8 * np); ++np; }
-        };
+        for (int j = 0; j < 2 * kRMax + 1; ++j) ev[j] = (j <= 2 * r) ? (c0 - (uint32_t)j) - sm.code[crow + j] : 0xFFFFFFFFu;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const uint32_t w = sm.slot[cb - (t >> 1) * kCW - (t & 1)];
-            const uint32_t b0 = w & 0xFFu, b1 = (w >> 8) & 0xFFu;
-            uint32_t l = min(b0, b1);
-            const uint32_t h = max(b0, b1);       // kSlotEmpty is larger than every code
-            if ((w & 0x00FF0000u) != 0x00FF0000u) {   // three or four contributors, or the overflow mark
-                const uint32_t b2 = (w >> 16) & 0xFFu, b3 = w >> 24;
-                if (b3 == kSlotOverflow) slow = true;
-                const uint32_t m2 = min(b2, b3), M2 = max(b2, b3);
-                const uint32_t t1 = max(l, m2), t2 = min(h, M2), s3 = max(h, M2);
-                l = min(l, m2);
-                push(min(t1, t2), t);
-                push(max(t1, t2), t);
-                if (s3 != kSlotEmpty) push(s3, t);
-            } else if (h != kSlotEmpty) {
-                push(h, t);
+        for (int j = 0; j < 2 * kRMax + 1; ++j) {
+            const uint32_t e = ev[j];
+            if (e & 0xFFFEFFFEu) continue;
+            const int cell = crow + j;
+            const float2 f = sm.frac[cell];
+            // east/south = frac, west/north = 1 - frac: bit-identical to the forward's (x0 + 1) - ix for every
+            // in-image tap (both are exact for x0 >= 1, and the same expression for x0 == 0)
+            const float wx = (e & 1u) ? f.x : __fsub_rn(1.0f, f.x);
+            const float wy = (e >> 16) ? f.y : __fsub_rn(1.0f, f.y);
+            const float w = __fmul_rn(wx, wy);
+            if (want_lay) {
+                float v[K];
+                load_px_smem<float, K>(sm.lay + (size_t)((ty + kRMax + dy) * kQW + tx + kRMax - r + j) * K, v);
+                fma2_bcast<K>(acc_l, v, w);
             }
-            lo[t] = l;
-        }
-        if (!slow) {
+            if (want_rgb) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int a = t & 1, b = t >> 1;
-                if (lo[t] != kSlotEmpty) hit(ty - b + kRMax + (int)(lo[t] >> 3) - 2, tx - a + kQX2 + (int)(lo[t] & 7u) - 2, a != 0, b != 0);
-            }
-            for (int i = 0; i < np; ++i) {
-                const uint32_t e = (uint32_t)(pend >> (8 * i)) & 0xFFu;
-                const int a = (int)(e >> 6) & 1, b = (int)(e >> 7);
-                hit(ty - b + kRMax + (int)((e >> 3) & 7u) - 2, tx - a + kQX2 + (int)(e & 7u) - 2, a != 0, b != 0);
-            }
-        } else {
-            // a neighbouring cell has more than four contributors: scan every candidate of the window in raster order
-            // candidate output pixel (sx + ddx, sy + dy) sits at window cell (ty + kRMax + dy, tx + kQX2 + ddx).  With its
-            // record code = (x0 - x + 8) | (y0 - y + 8) << 16,
-            //   e = ((8 - ddx) | (8 - dy) << 16) - code = (sx - x0) | (sy - y0) << 16:
-            // a hit iff both differences are 0 (west / north tap) or 1 (east / south tap); any other difference
-            // (incl. borrows, and code 0) leaves a bit outside {0, 16}.
-            for (int dy = -kRMax; dy <= kRMax; ++dy) {
-                const int crow = (ty + kRMax + dy) * kQW2 + tx + kQX2 - kRMax;
-                const uint32_t c0 = (uint32_t)(8 + kRMax) | ((uint32_t)(8 - dy) << 16);
-                for (int j = 0; j < 2 * kRMax + 1; ++j) {
-                    const uint32_t e = (c0 - (uint32_t)j) - sm.code[crow + j];
-                    if (e & 0xFFFEFFFEu) continue;
-                    hit(ty + kRMax + dy, tx + kQX2 - kRMax + j, (e & 1u) != 0u, (e >> 16) != 0u);
-                }
+                for (int c = 0; c < 3; ++c) acc_r[c] = fmaf(w, sm.rgb[cell * 3 + c], acc_r[c]);
             }
         }
     }
@@ -473,15 +368,16 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Param
     if (live && want_rgb) store_px<T, 3>(reinterpret_cast<T *>(p.d_src_rgb) + so * 3, acc_r);
     if (want_lay) {
         // transpose through shared memory: each warp writes its tile row (32 px x K, contiguous in HBM)
-        // as one bulk copy
+        // as consecutive 16-byte words
         __syncthreads();                                   // all gathers done: the d_out staging can be reused
         T *s_out = reinterpret_cast<T *>(sm.lay);          // [kThreads][K]
-        if (live) store_px<T, K>(s_out + (size_t)tid * K, acc_l);
+        if (live) store_px<T, K>(s_out + (size_t)(ty * kTW + tx) * K, acc_l);
         fence_async_smem();                                // the rows leave through the async proxy
-        __syncwarp();
-        if (sy < H) {                                      // warp-uniform: warp w owns tile row w (kTW == 32)
+        __syncthreads();                                   // a row holds pixels of four warps (patch mapping)
+        const int sy_w = ty0 + wid;                        // warp w owns tile row w (kTW == 32)
+        if (sy_w < H) {
             const int npx = min(kTW, W - tx0);
-            T *grow = reinterpret_cast<T *>(p.d_src_lay) + (img_px + (int64_t)sy * W + tx0) * K;
+            T *grow = reinterpret_cast<T *>(p.d_src_lay) + (img_px + (int64_t)sy_w * W + tx0) * K;
             const T *srow = s_out + (size_t)wid * kTW * K;
             const unsigned row_bytes = (unsigned)(npx * K * (int)sizeof(T));
             if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(grow) & 15) == 0) {
