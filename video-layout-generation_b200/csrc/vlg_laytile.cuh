@@ -39,6 +39,16 @@ template <> __device__ __forceinline__ float4 load4_smem<__nv_bfloat16>(const __
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// four consecutive channels from global memory (read-only path) as fp32
+template <typename T> __device__ __forceinline__ float4 load4_global(const T *p);
+template <> __device__ __forceinline__ float4 load4_global<float>(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+template <> __device__ __forceinline__ float4 load4_global<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162 *>(&r.x), hi = *reinterpret_cast<const __nv_bfloat162 *>(&r.y);
+    const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 constexpr int kLayMaxWarps = 8192;    // partial-sum rows reserved in the workspace (one per CTA of the persistent grid)
 
 struct LayParams {
@@ -300,13 +310,17 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         const float L2E = 1.4426950408889634f;
         const float cce = (GRAD && lab_ok && inside) ? ce_unit * wl : 0.0f;
         const T *st0 = nullptr;
+        (void)src_lay;
         {
             const unsigned rx = (unsigned)(tp.x0 - sm.org[b][0]), ry = (unsigned)(tp.y0 - sm.org[b][1]);
             if (inside && rx < (unsigned)(kTSW - 1) && ry < (unsigned)(kTSH - 1)) st0 = sm.win[b] + (ry * kTSW + rx) * K;
         }
-        if (st0) {
-            const T *st1 = st0 + kTSW * K;
-            vl[0] = to_f<T>(st0[il]); vl[1] = to_f<T>(st0[K + il]); vl[2] = to_f<T>(st1[il]); vl[3] = to_f<T>(st1[K + il]);
+        // One sweep for both sources of the taps: ld4(tap, c) hands channels 4c .. 4c+3 of tap 0..3 (nw, ne, sw, se),
+        // ld1(tap) its label channel.  Staged window: plain shared-memory loads (out-of-image cells hold the TMA's zeros).
+        // Taps outside the window (rare for smooth flow, the rule for rough flow such as BASELINE config 5): the same
+        // sweep on global loads, out-of-image taps read as zeros -- every tap is still fetched once.
+        auto sweep = [&](auto ld4, auto ld1) {
+            vl[0] = ld1(0); vl[1] = ld1(1); vl[2] = ld1(2); vl[3] = ld1(3);
             const float2 nw2 = make_float2(tp.nw, tp.nw), ne2 = make_float2(tp.ne, tp.ne);
             const float2 sw2 = make_float2(tp.sw, tp.sw), se2 = make_float2(tp.se, tp.se);
             float m_run = -3.0e38f;
@@ -317,8 +331,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
             se = 0.f;
 #pragma unroll
             for (int c = 0; c < K / 4; ++c) {
-                const float4 a = load4_smem<T>(st0 + 4 * c), bq = load4_smem<T>(st0 + K + 4 * c);
-                const float4 cq = load4_smem<T>(st1 + 4 * c), dq = load4_smem<T>(st1 + K + 4 * c);
+                const float4 a = ld4(0, c), bq = ld4(1, c), cq = ld4(2, c), dq = ld4(3, c);
                 // bit-exact FMA chain of Appendix A.6 on channel pairs
                 float2 z01 = __fmul2_rn(make_float2(a.x, a.y), nw2), z23 = __fmul2_rn(make_float2(a.z, a.w), nw2);
                 z01 = __ffma2_rn(make_float2(bq.x, bq.y), ne2, z01); z23 = __ffma2_rn(make_float2(bq.z, bq.w), ne2, z23);
@@ -366,36 +379,19 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
                 gix = (dne - dnw) * wy0 + (dse - dsw) * wy1;
                 giy = (dsw - dnw) * wx0 + (dse - dne) * wx1;
             }
+        };
+        if (st0) {
+            const T *st1 = st0 + kTSW * K;
+            sweep([&](int tap, int c) { return load4_smem<T>((tap & 2 ? st1 : st0) + (tap & 1) * K + 4 * c); },
+                  [&](int tap) { return to_f<T>(((tap & 2) ? st1 : st0)[(tap & 1) * K + il]); });
         } else {
-            // taps outside the staged window (rare): global gather, two sweeps, same FMA chain
-            gather_px<T, K>(src_lay, cc, tp, z);
-            vl[0] = tap_global<T>(src_lay, K, il, tp.y0, tp.x0, H, W);
-            vl[1] = tap_global<T>(src_lay, K, il, tp.y0, tp.x0 + 1, H, W);
-            vl[2] = tap_global<T>(src_lay, K, il, tp.y0 + 1, tp.x0, H, W);
-            vl[3] = tap_global<T>(src_lay, K, il, tp.y0 + 1, tp.x0 + 1, H, W);
-            zl = __fmaf_rn(vl[3], tp.se, __fmaf_rn(vl[2], tp.sw, __fmaf_rn(vl[1], tp.ne, __fmul_rn(vl[0], tp.nw))));
-            m = z[0];
-#pragma unroll
-            for (int k = 1; k < K; ++k) m = fmaxf(m, z[k]);
-            if (p.out_argmax && inside) {
-                int best = K - 1;
-#pragma unroll
-                for (int k = K - 2; k >= 0; --k) best = (z[k] == m) ? k : best;
-                p.out_argmax[img + (int64_t)y * W + x] = best;
-            }
-            const float ml2 = m * L2E;
-            se = 0.f;
-#pragma unroll
-            for (int k = 0; k < K; ++k) { z[k] = ex2_approx(fmaf(z[k], L2E, -ml2)); se += z[k]; }
-            if (GRAD) {
-                const float inv = cce * rcp_approx(se);
-                mul2_bcast<K>(z, z, inv);
-                gl = fmaf(ex2_approx((zl - m) * L2E), inv, -cce);
-                float gfull[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) gfull[k] = z[k] - (k == il ? cce : 0.0f);
-                coord_grad_px<T, K>(src_lay, cc, tp, gfull, gix, giy);
-            }
+            const T *g0 = src_lay + ((int64_t)tp.y0 * W + tp.x0) * K, *g1 = g0 + (int64_t)W * K;
+            const bool xin0 = tp.x0 >= 0 && tp.x0 < W, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < W;
+            const bool yin0 = tp.y0 >= 0 && tp.y0 < H, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < H;
+            const unsigned tin = (unsigned)(inside && yin0 && xin0) | ((unsigned)(inside && yin0 && xin1) << 1) |
+                                 ((unsigned)(inside && yin1 && xin0) << 2) | ((unsigned)(inside && yin1 && xin1) << 3);
+            sweep([&](int tap, int c) { return (tin >> tap) & 1u ? load4_global<T>((tap & 2 ? g1 : g0) + (tap & 1) * K + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); },
+                  [&](int tap) { return (tin >> tap) & 1u ? to_f<T>(__ldg(((tap & 2) ? g1 : g0) + (tap & 1) * K + il)) : 0.0f; });
         }
         if (lab_ok && inside) s_ce += wl * (fmaf(lg2_approx(se), 0.6931471805599453f, m) - zl);
         if (GRAD) {
