@@ -121,6 +121,7 @@ static int check_problem(const vlg_problem_t *p) {
     if (p->N < 1 || p->H < 2 || p->W < 2) return fail(VLG_ERR_ARG, "need N>=1, H>=2, W>=2 (got %lld,%lld,%lld)", (long long)p->N, (long long)p->H, (long long)p->W);
     if (p->N * p->H * p->W >= (1ll << 31)) return fail(VLG_ERR_UNSUPPORTED, "N*H*W must be < 2^31");
     if (p->N > 65535 || (p->H + 7) / 8 > 65535) return fail(VLG_ERR_UNSUPPORTED, "N and H/8 must fit a CUDA grid dimension (65535)");
+    if (p->H > 65000 || p->W > 65000) return fail(VLG_ERR_UNSUPPORTED, "H and W must be <= 65000 (16-bit tap cells in the far-pixel queue)");
     if (!k_supported(p->K)) return fail(VLG_ERR_UNSUPPORTED, "K=%lld not compiled in (see VLG_FOR_EACH_K)", (long long)p->K);
     if (p->dtype != VLG_F32 && p->dtype != VLG_BF16) return fail(VLG_ERR_ARG, "bad dtype %d", p->dtype);
     if (p->padding != VLG_PAD_ZEROS && p->padding != VLG_PAD_BORDER) return fail(VLG_ERR_ARG, "bad padding %d", p->padding);
@@ -154,7 +155,7 @@ static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
         L.rec_frac = off; off = align_up(off + Pp * sizeof(float2), 256);
         if (!(p->flags & VLG_FLAG_NO_FAR_PATH)) {
             L.far_acc = off; off = align_up(off + P * (3 + p->K) * sizeof(long long), 256);
-            L.far_list = off; off = align_up(off + P * sizeof(int), 256);
+            L.far_list = off; off = align_up(off + P * sizeof(int4), 256);
         }
     }
     L.total = off;
@@ -749,7 +750,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.partials = (float *)(ws + L.partials);
     pp.tile_disp = (float *)(ws + L.tile_disp);
     pp.tile_flags = (uint32_t *)(ws + L.tile_flags);
-    pp.far_list = (warp && d_out_lay && L.far_list) ? (int *)(ws + L.far_list) : nullptr;
+    pp.far_list = (warp && d_out_lay && L.far_list) ? (int4 *)(ws + L.far_list) : nullptr;
     pp.flagged_list = (int *)(ws + L.flagged);
     pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
     pp.hdr = hdr;
@@ -1101,7 +1102,7 @@ int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src
     pp.pitch = (int)L.pitch;
     pp.d_src_rgb = d_src_rgb; pp.d_src_lay = d_src_layout;
     pp.far_acc = L.far_acc ? (long long *)(ws + L.far_acc) : nullptr;
-    pp.far_list = L.far_list ? (const int *)(ws + L.far_list) : nullptr;
+    pp.far_list = L.far_list ? (const int4 *)(ws + L.far_list) : nullptr;
     pp.tile_flags = (const uint32_t *)(ws + L.tile_flags);
     pp.flagged_list = (const int *)(ws + L.flagged);
     pp.hdr = (WsHeader *)(ws + L.header);

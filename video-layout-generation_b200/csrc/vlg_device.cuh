@@ -452,6 +452,17 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// ---------------------------------------------------------------- tuning builds: when do the CTAs of a persistent kernel start / finish?
+#ifdef VLG_PROFILE_TAIL
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// slots: [0] first start, [1] last start, [2] first end, [3] last end (prof must be pre-set to {~0, 0, ~0, 0})
+__device__ __forceinline__ void prof_mark(unsigned long long *slot4, bool end) {
+    const unsigned long long t = global_ns();
+    atomicMin(slot4 + (end ? 2 : 0), t);
+    atomicMax(slot4 + (end ? 3 : 1), t);
+}
+#endif
+
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -53,7 +53,7 @@ struct Pass1Params {
     int64_t *out_argmax;    // nullable
     float *partials;        // [n_blocks][kPartialSlots]
     float *tile_disp;       // [n_blocks] max displacement among the tile's NEAR output pixels (WARP)
-    int *far_list;          // [P] compacted indices of FAR output pixels (nullable: no source gradient / no far path)
+    int4 *far_list;         // [P] queue of FAR output pixels: {pixel index, tap cell, fractional weights} (nullable: no source gradient / no far path)
     uint32_t *tile_flags;   // [n_blocks] != 0 where a far pixel lands in that SOURCE tile (zeroed with the header)
     int *flagged_list;      // [n_blocks] compacted ids of the flagged source tiles
     ReduceParams red;       // red.out != NULL: the last CTA also performs the final reduction
@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
             if (m_disp >= (float)VLG_NEAR_RADIUS && p.d_out_lay != nullptr) {
                 // far pixel (rare): queue it for the fixed-point scatter and flag the source tiles it hits
                 if (p.far_list) {
-                    p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = (int)(img_px + o);
+                    p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = make_int4((int)(img_px + o), (t.x0 + 8) | ((t.y0 + 8) << 16),
+                                                                              __float_as_int(t.ix - t.fx0), __float_as_int(t.iy - t.fy0));
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const int xx = t.x0 + (k4 & 1), yy = t.y0 + (k4 >> 1);

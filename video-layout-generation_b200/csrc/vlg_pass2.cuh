@@ -31,7 +31,7 @@ struct Pass2Params {
     void *d_src_rgb;          // type T, nullable
     void *d_src_lay;
     long long *far_acc;       // [P][3+K] fixed point, nullable (VLG_FLAG_NO_FAR_PATH)
-    const int *far_list;      // [far_count] far output pixels queued by pass 1
+    const int4 *far_list;     // [far_count] far output pixels queued by pass 1: {pixel index, (x0 + 8) | (y0 + 8) << 16, bits of ix - x0, bits of iy - y0}
     const uint32_t *tile_flags;  // [n_blocks] source tiles that receive far contributions
     const int *flagged_list;  // [n_flagged] ids of those tiles
     const float *tile_disp;   // [n_blocks] per-tile max NEAR displacement written by pass 1
@@ -59,13 +59,14 @@ __device__ __forceinline__ int near_radius(const Pass2Params &p, int n, int tyi,
 }
 
 // 2^e such that (sum of <= H*W contributions of magnitude <= maxgrad) * 2^e < 2^62
-__device__ __forceinline__ double far_scale(const WsHeader *hdr, int64_t HW) {
+__device__ __forceinline__ int far_scale_exp(const WsHeader *hdr, int64_t HW) {
     const float g = __uint_as_float(hdr->maxgrad_bits);
     int eg = 0, ehw = 0;
     frexpf(fmaxf(g, 1e-37f), &eg);
     frexp((double)HW, &ehw);
-    return ldexp(1.0, 61 - eg - ehw);
+    return min(61 - eg - ehw, 96);   // capped so that 2^e is an fp32 number too (gradients below 2^-96 are noise anyway)
 }
+__device__ __forceinline__ double far_scale(const WsHeader *hdr, int64_t HW) { return ldexp(1.0, far_scale_exp(hdr, HW)); }
 
 template <int K>
 constexpr size_t pass2_smem_bytes() {
@@ -427,45 +428,53 @@ __global__ void __launch_bounds__(kThreads) far_zero_kernel(const Pass2Params p)
 }
 
 // ---- far path: fixed-point scatter of the queued far output pixels ----
-// One WARP per far pixel: its taps are derived once, then the lanes walk the 4 x (3 + K) (tap, channel)
-// contributions -- consecutive lanes hit consecutive 8-byte accumulators of one source pixel, so every warp
-// instruction is one coalesced run of integer atomics.  The integer atomics are associative, so neither
-// the queue order nor the thread schedule can change the sums.  (The first version spent one THREAD per
-// contribution and ~400 instructions of index arithmetic on each: 11.6 ms for the 6 M far pixels of the
-// large-displacement configuration.)
+// One WARP per far pixel, lanes = the 3 + K channels of d_out (each lane loads its channel once), a warp-uniform
+// loop over the four taps: consecutive lanes hit consecutive 8-byte accumulators of one source pixel, so every
+// warp instruction is one coalesced run of integer atomics.  The integer atomics are associative, so neither
+// the queue order nor the thread schedule can change the sums.  The queue entry carries the tap cell and the
+// fractional weights pass 1 computed, so nothing is re-derived from the coordinates here.
+// (First version: one THREAD per contribution, ~400 instructions of index arithmetic each: 11.6 ms for the 6 M
+// far pixels of BASELINE config 5.  Second: one warp per pixel, lanes = (tap, channel) pairs, taps re-derived by
+// make_taps, fp64 scaling: 273 instructions per pixel, 2.56 ms.)
 template <int K>
 __global__ void __launch_bounds__(kThreads) far_scatter_kernel(const Pass2Params p) {
     const unsigned n_far = p.hdr->far_count;
     if (n_far == 0) return;
-    const CoordCfg &cc = p.cc;
-    const int H = cc.H, W = cc.W;
-    constexpr int CH = 3 + K, PER_PX = 4 * CH;
-    const double scale = far_scale(p.hdr, p.HW);
-    const float2 *coords = reinterpret_cast<const float2 *>(p.coords);
+    const int H = p.cc.H, W = p.cc.W;
+    constexpr int CH = 3 + K;
+    static_assert(CH <= 32 || CH <= 64, "channels are walked in at most two lane rounds");
+    const float scale = ldexpf(1.0f, far_scale_exp(p.hdr, p.HW));    // a power of two: v * scale is exact in fp32
     const unsigned lane = threadIdx.x & 31;
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned HWu = (unsigned)p.HW;
     for (unsigned j = gw; j < n_far; j += nw) {
-        const unsigned i = (unsigned)p.far_list[j];          // pixel index < 2^31 (check_problem)
+        const int4 e = __ldg(p.far_list + j);
+        const unsigned i = (unsigned)e.x;                    // pixel index < 2^31 (check_problem)
         const unsigned n = i / HWu, rem = i - n * HWu;
         const int y = (int)(rem / (unsigned)W), x = (int)(rem - (unsigned)y * (unsigned)W);
-        const Taps t = make_taps(cc, __ldg(coords + i), y, x);
+        const int x0 = (int)((unsigned)e.y & 0xFFFFu) - 8, y0 = (int)((unsigned)e.y >> 16) - 8;
+        const float fx = __int_as_float(e.z), fy = __int_as_float(e.w);
+        // east/south = frac, west/north = 1 - frac: the weights of the near path (pass2_rec_kernel), bit-identical to the
+        // forward's for every in-image tap
+        const float wx[2] = {__fsub_rn(1.0f, fx), fx}, wy[2] = {__fsub_rn(1.0f, fy), fy};
         const float *drgb = p.d_out_rgb ? p.d_out_rgb + (((int64_t)n * H + y) * p.pitch + x) * 3 : nullptr;
         const float *dlay = p.d_out_lay ? p.d_out_lay + (int64_t)i * K : nullptr;
         long long *img_acc = p.far_acc + (int64_t)n * p.HW * CH;
 #pragma unroll
-        for (int u0 = 0; u0 < PER_PX; u0 += 32) {
-            const int u = u0 + (int)lane;
-            if (u >= PER_PX) break;
-            const int k4 = u / CH, c = u - k4 * CH;
-            const int xs = t.x0 + (k4 & 1), ys = t.y0 + (k4 >> 1);
-            if (xs < 0 || xs >= W || ys < 0 || ys >= H) continue;
-            const float wt = k4 == 0 ? t.nw : k4 == 1 ? t.ne : k4 == 2 ? t.sw : t.se;
+        for (int c0 = 0; c0 < CH; c0 += 32) {
+            const int c = c0 + (int)lane;
             const float *src = c < 3 ? drgb : dlay;
-            if (!src) continue;
-            const float d = __ldg(src + (c < 3 ? c : c - 3));
-            unsigned long long *dst = reinterpret_cast<unsigned long long *>(img_acc + ((int64_t)ys * W + xs) * CH + c);
-            atomicAdd(dst, (unsigned long long)__double2ll_rn((double)__fmul_rn(wt, d) * scale));
+            float d = 0.f;
+            const bool have = c < CH && src != nullptr;
+            if (have) d = __ldg(src + (c < 3 ? c : c - 3));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const int xs = x0 + (k4 & 1), ys = y0 + (k4 >> 1);
+                if (xs < 0 || xs >= W || ys < 0 || ys >= H || !have) continue;      // warp-uniform but for `have`
+                const float wt = __fmul_rn(wx[k4 & 1], wy[k4 >> 1]);
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(img_acc + ((int64_t)ys * W + xs) * CH + c);
+                atomicAdd(dst, (unsigned long long)__float2ll_rn(__fmul_rn(__fmul_rn(wt, d), scale)));
+            }
         }
     }
 }
