@@ -588,6 +588,41 @@ def sweep_entry(cx, wl, N, steps, peak, note=None):
         return {"workload": wl, "batch": N, "error": str(exc)[:200]}
 
 
+def sweep_variants_c2(cx, peak):
+    """The two variants of the C2 step in which the sources are DATA, as in the reference's own data flow (the layout
+    source is one_hot(label), src/trainer.py:461; no gradient is asked for the sources): no pass 2, no d_out staging.
+      flow_grad_only : dense one-hot layout source, gradient to the flow only            128 algorithmic B/px
+      label_source   : int64 class-id map as the layout source (vlg_warp_loss_labels_*)   56 algorithmic B/px
+                       (coords 8 + rgb 12 + 12 + src label 8 + tgt label 8 read, d_flow 8 written)"""
+    out = {}
+    try:
+        fz = Fused(cx, "c2", WORKLOADS["c2"][0], with_src=False)
+        ms, r, total = cx.timed(fz.step, 5, min_ms=120.0)
+        out["c2_flow_grad_only"] = {"ms_per_step": ms, "Mpixel_per_s": cx.world * fz.P / (ms * 1e-3) / 1e6, "algorithmic_bytes_per_px": 128,
+                                    "frac_of_hbm_roofline": fz.P * 128 / (ms * 1e-3) / 1e9 / peak}
+        # label source: same inputs, the layout source handed over as its class-id map
+        ops, lib, ptr = cx.ops, cx.lib, cx.ops._ptr
+        labs = [s["src_layout"].argmax(1).contiguous() for s in fz.sets]
+        prob = ops._problem(fz.N, fz.H, fz.W, fz.K, fz.tdt, ops.WarpLossConfig(w_tv=0.5))
+        ws = ops._workspace(prob, False, cx.dev, cached=False)
+        sp = C.c_void_p(cx.stream.cuda_stream)
+
+        def lab_step(i):
+            s = fz.sets[i % len(fz.sets)]
+            ops.check(lib.vlg_warp_loss_labels_fwd_bwd(C.byref(prob), ptr(s["src_rgb"]), ptr(labs[i % len(labs)]), ptr(s["flow"]), ptr(s["tgt_rgb"]),
+                                                       ptr(s["tgt_label"]), ptr(fz.loss), ptr(fz.d_c), None, ptr(ws), ws.numel(), sp))
+        for i in range(3):
+            lab_step(i)
+        ms, r, total = cx.timed(lab_step, 5, min_ms=120.0)
+        out["c2_label_source"] = {"ms_per_step": ms, "Mpixel_per_s": cx.world * fz.P / (ms * 1e-3) / 1e6, "algorithmic_bytes_per_px": 56,
+                                  "frac_of_hbm_roofline": fz.P * 56 / (ms * 1e-3) / 1e9 / peak, "launch": "direct launches"}
+        fz.free()
+    except Exception as exc:
+        out["error"] = str(exc)[:200]
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -752,7 +787,7 @@ def main():
     # ---- the other BASELINE configs, compact (every rank takes part: weak scaling / per-rank rollout shards) ----
     sweep = None
     if not args.no_sweep and wl == "c2":
-        sweep = {}
+        sweep = sweep_variants_c2(cx, peak)
         sweep["c3"] = sweep_entry(cx, "c3", WORKLOADS["c3"][0], 5, peak)
         for B in (1, 4, 16, 64):
             sweep[f"c5_b{B}"] = sweep_entry(cx, "c5", B, 5, peak)

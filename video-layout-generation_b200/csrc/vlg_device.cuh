@@ -463,6 +463,23 @@ __device__ __forceinline__ void prof_mark(unsigned long long *slot4, bool end) {
 }
 #endif
 
+// ---------------------------------------------------------------- tuning builds: when do the units of a persistent kernel finish?
+// (tools/tail_prof.py; -DVLG_PROFILE_TAIL)
+#ifdef VLG_PROFILE_TAIL
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// (SM id << 24) | (ns timer / 16, 24 bits): where and when a unit of work finished
+__device__ __forceinline__ unsigned prof_stamp() {
+    unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    return (sm << 24) | (unsigned)((global_ns() >> 4) & 0xFFFFFFull);
+}
+// slots (zero-initialised with the header): [0] ~(first start), [1] last start, [2] ~(first end), [3] last end
+__device__ __forceinline__ void prof_mark(unsigned long long *slot4, bool end) {
+    const unsigned long long t = global_ns();
+    atomicMax(slot4 + (end ? 2 : 0), ~t);
+    atomicMax(slot4 + (end ? 3 : 1), t);
+}
+#endif
+
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -209,6 +209,9 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
     };
 
     // ---------------- prologue ----------------
+#ifdef VLG_PROFILE_TAIL
+    if (tid == 0) prof_mark(p.hdr->prof + 4, false);
+#endif
     if (tid < 2) { mbar_init(&sm.bar[tid], 1); sm.cnt[tid] = 0u; }
     if (tid < 8) sm.acc[tid >> 2][tid & 3] = 0;
     float2 f0 = load_coords(0, g0), f1 = load_coords(1, g1);
@@ -469,6 +472,9 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int w = 0; w < kTH; ++w) { o.x += sm.red[w][0]; o.y += sm.red[w][1]; o.z += sm.red[w][2]; }
+#ifdef VLG_PROFILE_TAIL
+        o.w = __uint_as_float(prof_stamp());     // where and when this CTA finished
+#endif
         reinterpret_cast<float4 *>(p.partials)[blockIdx.x] = o;
         if (blockIdx.x == 0) p.hdr->n_lay = gridDim.x;
         __threadfence();

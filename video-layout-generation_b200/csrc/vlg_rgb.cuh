@@ -71,8 +71,9 @@ __device__ __forceinline__ void rgb_issue_row(RgbRow &r, const CoordCfg &cc, flo
         float mx, my;
         const float2 xy = source_xy(cc, fl, bxv, base_coord(t, cc.Hm1), mx, my);
         const Taps tp = taps_from_xy(cc, xy, mx, my);
-        const int x0c = min(max(tp.x0, 0), W - 1), x1c = min(max(tp.x0 + 1, 0), W - 1);
-        const int y0c = min(max(tp.y0, 0), H - 1), y1c = min(max(tp.y0 + 1, 0), H - 1);
+        // border padding: the position was clipped into [0, S-1] before the floor, so only the far taps need a clamp
+        const int x0c = BORDER ? tp.x0 : min(max(tp.x0, 0), W - 1), x1c = BORDER ? min(tp.x0 + 1, W - 1) : min(max(tp.x0 + 1, 0), W - 1);
+        const int y0c = BORDER ? tp.y0 : min(max(tp.y0, 0), H - 1), y1c = BORDER ? min(tp.y0 + 1, H - 1) : min(max(tp.y0 + 1, 0), H - 1);
         load_px<T, 3>(src + (int64_t)(y0c * W + x0c) * 3, r.v[0]);
         load_px<T, 3>(src + (int64_t)(y0c * W + x1c) * 3, r.v[1]);
         load_px<T, 3>(src + (int64_t)(y1c * W + x0c) * 3, r.v[2]);
@@ -113,6 +114,9 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
     const unsigned FULL = 0xffffffffu;
 
     float s_l1 = 0.f, s_gd = 0.f, s_ssim = 0.f, m_grad = 0.f;
+#ifdef VLG_PROFILE_TAIL
+    if (lane == 0) prof_mark(p.hdr->prof, false);
+#endif
 
     const float inv9 = 1.0f / 9.0f, C1 = 1e-4f, C2 = 9e-4f;
     const float kk = -p.c_ssim * (2.0f / 9.0f);
@@ -142,16 +146,18 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
 
         // sliding state: index 1 = row t-1, index 2 = row t-2
         float a1[3] = {0.f, 0.f, 0.f}, b1[3] = {0.f, 0.f, 0.f}, a2[3] = {0.f, 0.f, 0.f}, b2[3] = {0.f, 0.f, 0.f};
-        float2 hs1[3], hs2[3], hq1[3], hq2[3];     // horizontal 3-sums of (a,b) and (a^2,b^2)
-        float hx1[3], hx2[3];                       // ... and of a*b
-        float QA1[3], QB1[3], QC1[3], QA2[3], QB2[3], QC2[3];   // horizontal 3-sums of the window coefficients
+        // vertical 3-sums are formed as (row t-2 + row t-1) + row t: the pair sum of the two previous rows is carried
+        // instead of row t-2 itself (same association, one register move less per quantity and row)
+        float2 hs1[3], hsP[3], hq1[3], hqP[3];     // horizontal 3-sums of (a,b) and (a^2,b^2): row t-1, rows (t-2) + (t-1)
+        float hx1[3], hxP[3];                       // ... and of a*b
+        float QA1[3], QB1[3], QC1[3], QAP[3], QBP[3], QCP[3];   // horizontal 3-sums of the window coefficients
         float G1[3], G2[3];                         // partial d(loss)/d(a) of rows t-1, t-2
         float Dx1[3], Dy1[3], Dx2[3], Dy2[3];       // d(a)/d(coord) of rows t-1, t-2 (mask and scale folded in)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            hs1[c] = hs2[c] = hq1[c] = hq2[c] = make_float2(0.f, 0.f);
-            hx1[c] = hx2[c] = 0.f;
-            QA1[c] = QB1[c] = QC1[c] = QA2[c] = QB2[c] = QC2[c] = 0.f;
+            hs1[c] = hsP[c] = hq1[c] = hqP[c] = make_float2(0.f, 0.f);
+            hx1[c] = hxP[c] = 0.f;
+            QA1[c] = QB1[c] = QC1[c] = QAP[c] = QBP[c] = QCP[c] = 0.f;
             G1[c] = G2[c] = 0.f;
             Dx1[c] = Dy1[c] = Dx2[c] = Dy2[c] = 0.f;
         }
@@ -237,9 +243,9 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                 hq0[c] = __ffma2_rn(pr, pr, __ffma2_rn(pc, pc, __fmul2_rn(pl, pl)));
                 hx0[c] = fmaf(ar, br, fmaf(a, b, al * bl));
                 // SSIM window centred on (x, t-1): rows t-2, t-1, t
-                const float2 S1 = __fadd2_rn(__fadd2_rn(hs2[c], hs1[c]), hs0[c]);
-                const float2 S2 = __fadd2_rn(__fadd2_rn(hq2[c], hq1[c]), hq0[c]);
-                const float Sxy = (hx2[c] + hx1[c]) + hx0[c];
+                const float2 S1 = __fadd2_rn(hsP[c], hs0[c]);
+                const float2 S2 = __fadd2_rn(hqP[c], hq0[c]);
+                const float Sxy = hxP[c] + hx0[c];
                 const float2 inv9_2 = make_float2(inv9, inv9);
                 const float2 m2 = __fmul2_rn(S1, inv9_2);                           // (mu_x, mu_y)
                 const float2 mm = __fmul2_rn(m2, m2);
@@ -271,8 +277,8 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                 float gx = 0.f, gy = 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float sA = (QA2[c] + QA1[c]) + QA0[c], sB = (QB2[c] + QB1[c]) + QB0[c];
-                    const float sC = (QC2[c] + QC1[c]) + QC0[c];
+                    const float sA = QAP[c] + QA0[c], sB = QBP[c] + QB0[c];
+                    const float sC = QCP[c] + QC0[c];
                     dr[c] = G2[c] + fmaf(sC, b2[c], fmaf(sB, a2[c], sA));
                     gx = fmaf(dr[c], Dx2[c], gx);
                     gy = fmaf(dr[c], Dy2[c], gy);
@@ -289,9 +295,13 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 a2[c] = a1[c]; b2[c] = b1[c]; a1[c] = a0[c]; b1[c] = b0[c];
-                hs2[c] = hs1[c]; hs1[c] = hs0[c]; hq2[c] = hq1[c]; hq1[c] = hq0[c]; hx2[c] = hx1[c]; hx1[c] = hx0[c];
+                hsP[c] = __fadd2_rn(hs1[c], hs0[c]); hs1[c] = hs0[c];
+                hqP[c] = __fadd2_rn(hq1[c], hq0[c]); hq1[c] = hq0[c];
+                hxP[c] = hx1[c] + hx0[c]; hx1[c] = hx0[c];
                 if (GRAD) {
-                    QA2[c] = QA1[c]; QA1[c] = QA0[c]; QB2[c] = QB1[c]; QB1[c] = QB0[c]; QC2[c] = QC1[c]; QC1[c] = QC0[c];
+                    QAP[c] = QA1[c] + QA0[c]; QA1[c] = QA0[c];
+                    QBP[c] = QB1[c] + QB0[c]; QB1[c] = QB0[c];
+                    QCP[c] = QC1[c] + QC0[c]; QC1[c] = QC0[c];
                     G2[c] = G1[c]; G1[c] = G0[c];
                     Dx2[c] = Dx1[c]; Dx1[c] = Dx0[c]; Dy2[c] = Dy1[c]; Dy1[c] = Dy0[c];
                 }
@@ -312,6 +322,9 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
         o.y = (p.terms & VLG_TERM_GD) ? s_gd : 0.f;
         o.z = (p.terms & VLG_TERM_SSIM) ? s_ssim : 0.f;
         o.w = 0.f;
+#ifdef VLG_PROFILE_TAIL
+        o.w = __uint_as_float(prof_stamp());     // where and when this warp finished
+#endif
         reinterpret_cast<float4 *>(p.partials)[gw] = o;
         if (m_grad > 0.f) atomicMax(&p.hdr->maxgrad_bits, __float_as_uint(m_grad));
         if (gw == 0) p.hdr->n_rgb = gridDim.x * (kRgbThreads / 32);
