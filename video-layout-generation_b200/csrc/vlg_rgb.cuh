@@ -173,11 +173,6 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
 
 #pragma unroll 1
         for (; t <= t_last; ++t) {
-            // ---- software pipeline: flow of row t+2, taps + target of row t+1 ----
-            const float2 fl_next2 = load_flow(t + 2);
-            RgbRow nxt;
-            rgb_issue_row<T, BORDER>(nxt, cc, fl_next, bxv, t + 1, xc, src, tgt, t + 1 >= 0 && t + 1 < H && t + 1 <= t_last);
-
             // ---- row t ----
             const bool row_ok = t >= 0 && t < H;
             const bool live = row_ok && col_ok;
@@ -211,6 +206,11 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                     }
                 }
             }
+            // ---- software pipeline: the raw taps of row t are consumed -- the taps + target of row t+1 are loaded into the
+            // same registers (no second row buffer, no copy) and travel while the rest of this iteration computes; the flow of
+            // row t+2 follows ----
+            rgb_issue_row<T, BORDER>(cur, cc, fl_next, bxv, t + 1, xc, src, tgt, t + 1 >= 0 && t + 1 < H && t + 1 <= t_last);
+            fl_next = load_flow(t + 2);
 
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -306,8 +306,6 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
                     Dx2[c] = Dx1[c]; Dx1[c] = Dx0[c]; Dy2[c] = Dy1[c]; Dy1[c] = Dy0[c];
                 }
             }
-            cur = nxt;
-            fl_next = fl_next2;
         }
     }
 
