@@ -127,3 +127,24 @@ def test_renorm_oracle_follows_trainer_expressions():
     out, lab = TO.renorm_frames(frame, flip=True, labels=seg)
     assert torch.equal(out, torch.flip(want, [3])) and torch.equal(lab, torch.flip(seg, [2]))
     assert torch.equal(TO.renorm_frames(want, denormalize=True), want * img_std_arr + img_mean_arr)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) needs no GPU: one JSON line with the
+    contract's keys, our arm's workload description, and a cpu_baseline describing the run."""
+    import json
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Mpixel/s" and d["value"] > 0
+    assert d["config"]["workload"].startswith("c1: 2x128x256") and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

@@ -38,5 +38,12 @@ for (N, H, W, sigma, far) in ((1, 37, 70, 1.5, 0.0), (2, 24, 45, 6.0, 0.05)):
     for kw in (dict(pass2_records=False), dict(layout_kernel="tile"), dict(tile_kernels=True)):
         total, _, _ = vlg_b200.warp_loss(a, b, f, t, lab, vlg_b200.WarpLossConfig(w_tv=0.5, **kw))
         total.backward()
+    # label-source op and uint8 ingest
+    total, _, _ = vlg_b200.warp_loss(a.detach(), lab, f, t, lab, vlg_b200.WarpLossConfig(w_tv=0.5, want_argmax=True))
+    total.backward()
+    u8 = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, device=dev)
+    s8 = torch.randint(0, K, (N, H, W), dtype=torch.uint8, device=dev)
+    vlg_b200.ingest(u8, s8, flip=True, n_classes=K, want_label=True, want_seg_float=True, want_one_hot=True)
+    vlg_b200.ingest(u8, s8, n_classes=K, dtype=torch.bfloat16, want_one_hot=True)
 torch.cuda.synchronize()
 print("sanitize case done", float(total))
