@@ -397,13 +397,13 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
             sweep([&](int tap, int c) { return load4_smem<T>((tap & 2 ? st1 : st0) + (tap & 1) * K + 4 * c); },
                   [&](int tap) { return to_f<T>(((tap & 2) ? st1 : st0)[(tap & 1) * K + il]); });
         } else {
-            const T *g0 = src_lay + ((int64_t)tp.y0 * W + tp.x0) * K, *g1 = g0 + (int64_t)W * K;
+            const T *q0 = src_lay + ((int64_t)tp.y0 * W + tp.x0) * K, *q1 = q0 + (int64_t)W * K;
             const bool xin0 = tp.x0 >= 0 && tp.x0 < W, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < W;
             const bool yin0 = tp.y0 >= 0 && tp.y0 < H, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < H;
             const unsigned tin = (unsigned)(inside && yin0 && xin0) | ((unsigned)(inside && yin0 && xin1) << 1) |
                                  ((unsigned)(inside && yin1 && xin0) << 2) | ((unsigned)(inside && yin1 && xin1) << 3);
-            sweep([&](int tap, int c) { return (tin >> tap) & 1u ? load4_global<T>((tap & 2 ? g1 : g0) + (tap & 1) * K + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); },
-                  [&](int tap) { return (tin >> tap) & 1u ? to_f<T>(__ldg(((tap & 2) ? g1 : g0) + (tap & 1) * K + il)) : 0.0f; });
+            sweep([&](int tap, int c) { return (tin >> tap) & 1u ? load4_global<T>((tap & 2 ? q1 : q0) + (tap & 1) * K + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); },
+                  [&](int tap) { return (tin >> tap) & 1u ? to_f<T>(__ldg(((tap & 2) ? q1 : q0) + (tap & 1) * K + il)) : 0.0f; });
         }
         if (lab_ok && inside) s_ce += wl * (fmaf(lg2_approx(se), 0.6931471805599453f, m) - zl);
         if (GRAD) {
