@@ -455,6 +455,12 @@ def e2e_fused(cx: Ctx, fz: Fused, steps):
                 dbuf[j][k].copy_(v, non_blocking=True)
             up_done[j].record(copy_stream)
 
+    # results travel back the same way the inputs arrive: the loss vector of step i is copied into pinned host memory
+    # right behind its kernels and the host looks at it while step i+1 runs (one step in flight in each direction)
+    res_host = [torch.empty(cx.cabi.LOSS_SLOTS, dtype=torch.float32).pin_memory() for _ in range(2)]
+    res_done = [torch.cuda.Event(), torch.cuda.Event()]
+    seen = []
+
     def e2e_step(i):
         j = i & 1
         upload(j ^ 1)                      # inputs of the NEXT step
@@ -468,28 +474,41 @@ def e2e_fused(cx: Ctx, fz: Fused, steps):
         total = crit(a, b, f, tgt["frames"], tgt["label"])
         total.backward()
         consumed[j].record(stream)
-        return crit.last_terms.cpu()       # device -> host read of the step's result (synchronises)
+        res_host[j].copy_(crit.last_terms, non_blocking=True)     # device -> host read of the step's result
+        res_done[j].record(stream)
+        if i > 0:                          # the previous step's result has landed by now (or is waited for here)
+            res_done[j ^ 1].synchronize()
+            seen.append(float(res_host[j ^ 1][cx.cabi.LOSS_TOTAL]))
+
+    def drain(i_last):
+        res_done[i_last & 1].synchronize()
+        seen.append(float(res_host[i_last & 1][cx.cabi.LOSS_TOTAL]))
 
     for j in range(2):
         consumed[j].record(stream)
     upload(0)
     for i in range(4):
         e2e_step(i)
+    drain(3)
     cx.barrier()
     n = max(4, min(steps, 20)) & ~1
+    seen.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(n):
         e2e_step(i)
+    drain(n - 1)
     e1.record(stream)
     cx.barrier()
+    assert len(seen) == n and all(math.isfinite(v) for v in seen), "every step's result must have reached the host"
     ms = cx.max_over_ranks(e0.elapsed_time(e1) / n)
     return {"value": cx.world * fz.P / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": cx.cabi.LOSS_SLOTS * 4, "ms_per_step": ms, "steps": n,
             "inputs": "pinned host, what the dataset holds (src/folder.py:85-104): uint8 RGB frames [N,H,W,3] x2, uint8 class maps "
                       "[N,H,W] x2, fp32 flow = 16 B/px; on the device vlg_ingest turns them into normalised NHWC frames, int64 "
                       "labels and the one-hot source layout (ToTensor + renorm + one_hot, bit-identical), then WarpLoss + "
-                      "backward; the loss vector is read back every step; double-buffered uploads on a copy stream"}
+                      "backward; the loss vector of every step is copied back to pinned host memory and read there one step later; "
+                      "double-buffered uploads on a copy stream"}
 
 
 class Rollout:
