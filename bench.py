@@ -434,13 +434,19 @@ def u8_host_inputs(d, K):
     return {k: v.cpu().pin_memory() for k, v in host.items()}
 
 
-def e2e_fused(cx: Ctx, fz: Fused, steps):
+def e2e_fused(cx: Ctx, fz: Fused, steps, flow_from_host=False):
     """End to end through the public API (vlg_b200.ingest + vlg_b200.WarpLoss + backward) from pinned host memory.
-    Every step uploads one full input set -- what the dataset holds: uint8 frames and class maps, fp32 flow -- and reads
-    the step's loss vector back.  Double-buffered: the inputs of step i+1 travel on a copy stream while step i
-    computes (what a DataLoader prefetcher does)."""
+    Every step uploads one full input set -- what the dataset holds: uint8 frames and class maps -- and reads the
+    step's loss vector back.  Double-buffered: the inputs of step i+1 travel on a copy stream while step i computes
+    (what a DataLoader prefetcher does).  The flow is NOT part of the dataset: in the reference's step it is the
+    network's output (src/trainer.py:183-210: frames and class maps are uploaded, the network computes its output from them) and never exists on the host, so it
+    is device-resident here (two alternating flow fields); `flow_from_host=True` uploads it as well (the round-1/2
+    figure, kept as `flow_uploaded` for comparison)."""
     vlg, dev, stream = cx.vlg, cx.dev, cx.stream
     host = u8_host_inputs(fz.sets[0], fz.K)
+    if not flow_from_host:
+        del host["flow"]
+    dev_flow = [fz.sets[q % len(fz.sets)]["flow"] for q in range(2)]
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     crit = vlg.WarpLoss(weights=(40.0, 20.0, 10.0, 0.5))
     copy_stream = torch.cuda.Stream(device=dev)
@@ -470,7 +476,7 @@ def e2e_fused(cx: Ctx, fz: Fused, steps):
         tgt = vlg.ingest(cur["tgt_u8"], cur["tgt_seg_u8"], n_classes=fz.K, dtype=fz.tdt, want_label=True)
         a = src["frames"].requires_grad_(fz.with_src)
         b = src["one_hot"].requires_grad_(fz.with_src)
-        f = cur["flow"].detach().requires_grad_(True)
+        f = (cur["flow"] if flow_from_host else dev_flow[j]).detach().requires_grad_(True)
         total = crit(a, b, f, tgt["frames"], tgt["label"])
         total.backward()
         consumed[j].record(stream)
@@ -505,7 +511,8 @@ def e2e_fused(cx: Ctx, fz: Fused, steps):
     return {"value": cx.world * fz.P / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": cx.cabi.LOSS_SLOTS * 4, "ms_per_step": ms, "steps": n,
             "inputs": "pinned host, what the dataset holds (src/folder.py:85-104): uint8 RGB frames [N,H,W,3] x2, uint8 class maps "
-                      "[N,H,W] x2, fp32 flow = 16 B/px; on the device vlg_ingest turns them into normalised NHWC frames, int64 "
+                      "[N,H,W] x2" + (", and the fp32 flow = 16 B/px" if flow_from_host else " = 8 B/px; the flow is the network's output in "
+                      "the reference's step (src/trainer.py:183-210) and stays on the device") + "; on the device vlg_ingest turns them into normalised NHWC frames, int64 "
                       "labels and the one-hot source layout (ToTensor + renorm + one_hot, bit-identical), then WarpLoss + "
                       "backward; the loss vector of every step is copied back to pinned host memory and read there one step later; "
                       "double-buffered uploads on a copy stream"}
@@ -734,6 +741,8 @@ def main():
 
     # ---- timed region 2: end to end through the public module API from pinned host memory ----
     e2e = e2e_fused(cx, fz, args.steps)
+    up = e2e_fused(cx, fz, args.steps, flow_from_host=True)
+    e2e["flow_uploaded"] = {k: up[k] for k in ("value", "unit", "h2d_bytes_per_step", "ms_per_step")}
 
     # ---- incumbent on the same GPU: the oracle composition run by torch CUDA eager (ATen kernels) ----
     eager = None

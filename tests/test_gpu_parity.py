@@ -288,6 +288,66 @@ def test_compressive_flow_source_gradient_vs_oracle(padding):
     _assert_close_either(_nchw(b.grad), ref["d_src_layout"].numpy(), ref64["d_src_layout"].numpy(), RTOL, "d_src_layout")
 
 
+@pytest.mark.parametrize("packed", [True, False])
+@pytest.mark.parametrize("padding", ["border", "zeros"])
+def test_far_path_many_pixels_into_one_source_tile(padding, packed):
+    """The far path packs two 32-bit lanes into one 64-bit atomic in every source-tile row that receives at most 512 far
+    pixels and keeps one 64-bit accumulator per channel elsewhere (vlg_pass2.cuh).  Here every pixel of a 64x96 image
+    samples around the same few source pixels (6 000 far pixels into two tile rows: those rows run wide, the rest of
+    the image packed or empty) -- against the oracle at the parity bar (fp64 tie-breaker: thousands of contributions
+    meet in a handful of source pixels), bitwise reproducible, with and without VLG_FLAG_FAR_WIDE."""
+    N, H, W, K = 2, 64, 96, 20
+    d = _make_case(N, H, W, K, 0.3, seed=41, layout="soft")
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    tgt_x, tgt_y = 70.3, 11.6                                    # everybody looks at (70.3, 11.6) +- 1.5 px
+    d["flow"] = d["flow"] * 3.0 + torch.stack((tgt_x - xx, tgt_y - yy), -1)[None]
+    kw = dict(w_tv=0.2, padding_mode=padding)
+    ref = TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"], **kw)
+    ref64 = TO.warp_loss_fwd_bwd(d["src_rgb"], d["src_layout"], d["flow"], d["tgt_rgb"], d["tgt_label"], dtype=torch.float64, **kw)
+    outs = []
+    for _ in range(2):
+        a = _cl(d["src_rgb"]).requires_grad_(True)
+        b = _cl(d["src_layout"]).requires_grad_(True)
+        f = d["flow"].to(DEV).requires_grad_(True)
+        total, vec, _ = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV),
+                                           vlg_b200.WarpLossConfig(far_packed=packed, **kw))
+        total.backward()
+        outs.append((a.grad.clone(), b.grad.clone(), f.grad.clone()))
+    assert vec[_cabi.LOSS_MAXDISP].item() >= _cabi.NEAR_RADIUS
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    _assert_close_norm(_nchw(outs[0][2]), ref["d_flow"].numpy(), RTOL, "d_flow")
+    _assert_close_either(_nchw(outs[0][0]), ref["d_src_rgb"].numpy(), ref64["d_src_rgb"].numpy(), RTOL, "d_src_rgb")
+    _assert_close_either(_nchw(outs[0][1]), ref["d_src_layout"].numpy(), ref64["d_src_layout"].numpy(), RTOL, "d_src_layout")
+
+
+@pytest.mark.parametrize("padding", ["border", "zeros"])
+@pytest.mark.parametrize("sigma", [48.0, 150.0])
+def test_far_path_packed_lanes_agree_with_wide_accumulators(padding, sigma):
+    """Rough flow (most pixels far, a few per source-tile row): the packed 32-bit lanes round every contribution at
+    2^-(30-h) of its group's largest gradient (h = bits of the row's far-pixel count), the wide mode at ~2^-40.
+    Their results agree to 1e-6 of the largest gradient (a tenth of the parity bar) for the rgb AND the layout
+    group, whose gradients differ by orders of magnitude (separate scales); ragged shape, both paddings."""
+    N, H, W, K = 2, 61, 131, 20
+    d = _make_case(N, H, W, K, sigma, seed=43, layout="soft", far_frac=0.05)
+    kw = dict(w_tv=0.7, padding_mode=padding)
+    res = {}
+    for packed in (True, False):
+        a = _cl(d["src_rgb"]).requires_grad_(True)
+        b = _cl(d["src_layout"]).requires_grad_(True)
+        f = d["flow"].to(DEV).requires_grad_(True)
+        total, vec, _ = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV),
+                                           vlg_b200.WarpLossConfig(far_packed=packed, **kw))
+        total.backward()
+        res[packed] = (a.grad.clone(), b.grad.clone(), f.grad.clone(), vec.clone())
+    assert res[True][3][_cabi.LOSS_MAXDISP].item() >= _cabi.NEAR_RADIUS
+    assert torch.equal(res[True][2], res[False][2]) and torch.equal(res[True][3], res[False][3])
+    for i, name in ((0, "d_src_rgb"), (1, "d_src_layout")):
+        mx = res[False][i].abs().max().item()
+        err = (res[True][i] - res[False][i]).abs().max().item()
+        assert err <= 1e-6 * mx, f"{name}: packed vs wide {err / mx:.2e}"
+
+
 def test_upstream_gradient_scaling():
     d = _make_case(1, 40, 72, 20, 2.0, seed=3)
     grads = []

@@ -155,8 +155,12 @@ def test_reference_convention_reproduces_trainer_sync():
 
 def test_optimiser_step_matches_the_oracle_driven_step():
     """One Adam step of the harness's shape (train.py: producer -> fused op -> backward -> Adam) against the same step
-    with the oracle composition in torch CUDA autograd: loss to 1e-5, producer gradients to 1e-5, and the loss goes
-    down over a few steps."""
+    with the oracle composition in torch CUDA autograd: loss and the op's own gradient (d_flow) to 1e-5.  The producer's
+    WEIGHT gradients are sums over all pixels with heavy cancellation, reduced by cuDNN's backward kernels in their own
+    order, so two fp32 steps differ by ~1e-5 there whatever the op does: they are judged against the same step in fp64
+    (net, oracle and autograd in double) -- the fused op's step must be as close to it as the oracle-driven fp32 step is
+    (1e-5, or 1.5x the oracle-driven step's own distance, whichever is larger).  And the loss goes down over a few steps."""
+    import copy
     N, H, W, K = 2, 48, 80, 20
     b = _batch(N, H, W, K, seed=23)
     lay = vlg_b200.one_hot_layout(b["seg2"], K)
@@ -164,18 +168,31 @@ def test_optimiser_step_matches_the_oracle_driven_step():
     net = _small_net(seed=1)
     net_ref = _small_net(seed=1)
     net_ref.load_state_dict(net.state_dict())
+    net64 = copy.deepcopy(net).double()
     crit = vlg_b200.WarpLoss(weights=(40.0, 20.0, 10.0, 0.5))
 
     flow, _ = net(x)
-    loss = crit(b["frame2"], lay, flow_nhw2(flow), b["frame3"], b["seg3"])
+    f_op = flow_nhw2(flow)
+    f_op.retain_grad()
+    loss = crit(b["frame2"], lay, f_op, b["frame3"], b["seg3"])
     loss.backward()
 
     flow_r, _ = net_ref(x)
-    o = TO.warp_loss(b["frame2"], lay, flow_nhw2(flow_r), b["frame3"], b["seg3"], w_tv=0.5)
+    f_ref = flow_nhw2(flow_r)
+    f_ref.retain_grad()
+    o = TO.warp_loss(b["frame2"], lay, f_ref, b["frame3"], b["seg3"], w_tv=0.5)
     o["total"].backward()
     np.testing.assert_allclose(loss.item(), o["total"].item(), rtol=1e-5)
-    mx, rms = parity_errors(_grads(net), _grads(net_ref))
-    assert mx <= 1e-5 and rms <= 1e-5, (mx, rms)
+    mx, rms = parity_errors(f_op.grad, f_ref.grad)
+    assert mx <= 1e-5 and rms <= 1e-5, ("d_flow", mx, rms)
+
+    flow_d, _ = net64(x.double())
+    o64 = TO.warp_loss(b["frame2"].double(), lay.double(), flow_nhw2(flow_d), b["frame3"].double(), b["seg3"], w_tv=0.5)
+    o64["total"].backward()
+    g64 = _grads(net64)
+    ours, theirs = parity_errors(_grads(net), g64), parity_errors(_grads(net_ref), g64)
+    for got, ref, what in zip(ours, theirs, ("normwise-max", "RMS-relative")):
+        assert got <= max(1e-5, 1.5 * ref), (what, "fused step vs fp64", got, "oracle-driven fp32 step vs fp64", ref)
 
     opt = torch.optim.Adam(net.parameters(), lr=2e-3, betas=(0.5, 0.999))      # src/main.py:139-141
     first = None

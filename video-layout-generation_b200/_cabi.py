@@ -14,6 +14,7 @@ FLAG_NO_TMA = 2
 FLAG_TILE_RGB = 4
 FLAG_TILE_LAYOUT = 8
 FLAG_PASS2_COORDS = 32
+FLAG_FAR_WIDE = 64
 TERM_L1, TERM_GD, TERM_SSIM, TERM_CE, TERM_TV, TERM_ALL = 1, 2, 4, 8, 16, 31
 STATUS_BAD_LABEL, STATUS_FAR_TAPS = 1, 2
 CE_NORM_TORCH, CE_NORM_COUNT = 0, 1

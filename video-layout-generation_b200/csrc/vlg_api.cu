@@ -138,9 +138,11 @@ static WsLayout ws_layout(const vlg_problem_t *p, int with_src_grad) {
     L.n_blocks = p->N * tiles_x(p->W) * tiles_y(p->H);
     size_t off = 0;
     L.header = off; off = align_up(off + sizeof(WsHeader), 256);
-    // header, per-tile far flags and per-tile displacement maxima are contiguous: one memset resets all three
+    // header, per-tile far flags, per-tile displacement maxima and the far-pixel counts per tile row are contiguous: one memset
+    // resets them all
     L.tile_flags = off; off = align_up(off + (size_t)L.n_blocks * sizeof(uint32_t), 256);
     L.tile_disp = off; off = align_up(off + (size_t)L.n_blocks * sizeof(float), 256);
+    L.seg_cnt = off; off = align_up(off + (size_t)L.n_blocks * kTH * sizeof(uint32_t), 256);   // far pixels per SOURCE tile row
     L.partials = off; off = align_up(off + (size_t)L.n_blocks * kPartialSlots * sizeof(float), 256);
     L.partials_rgb = off; off = align_up(off + (size_t)kRgbMaxWarps * kRgbSlots * sizeof(float), 256);
     L.partials_lay = off; off = align_up(off + (size_t)kLayMaxWarps * 4 * sizeof(float), 256);
@@ -547,7 +549,7 @@ static int launch_pass2(Pass2Params pp, int64_t n_blocks, int64_t P, const vlg_p
         far_zero_kernel<K><<<sms * 2, kThreads, 0, st>>>(pp);
         int rc = check_launch("far_zero_kernel");
         if (rc) return rc;
-        far_scatter_kernel<K><<<sms * 4, kThreads, 0, st>>>(pp);
+        far_scatter_kernel<K><<<sms * VLG_FAR_CTAS, kThreads, 0, st>>>(pp);
         rc = check_launch("far_scatter_kernel");
         if (rc) return rc;
     }
@@ -750,6 +752,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
     pp.partials = (float *)(ws + L.partials);
     pp.tile_disp = (float *)(ws + L.tile_disp);
     pp.tile_flags = (uint32_t *)(ws + L.tile_flags);
+    pp.seg_cnt = (prob->flags & VLG_FLAG_FAR_WIDE) ? nullptr : (uint32_t *)(ws + L.seg_cnt);
     pp.far_list = (warp && d_out_lay && L.far_list) ? (int4 *)(ws + L.far_list) : nullptr;
     pp.flagged_list = (int *)(ws + L.flagged);
     pp.red = make_reduce_params(prob, L, ws, fused_loss_out);
@@ -809,7 +812,7 @@ static int run_pass1(const vlg_problem_t *prob, bool warp, const void *src_rgb, 
             }
             lp.out_argmax = out_argmax;
             lp.partials = (float *)(ws + L.partials_lay);
-            lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.flagged_list = pp.flagged_list;
+            lp.tile_disp = pp.tile_disp; lp.far_list = pp.far_list; lp.tile_flags = pp.tile_flags; lp.seg_cnt = pp.seg_cnt; lp.flagged_list = pp.flagged_list;
             lp.red = pp.red; lp.hdr = hdr;
             tl_mark(kTlLay0, st);
             rc = dispatch_laytile(prob, lp, row_map, px8, need_grad, st);
@@ -1104,6 +1107,7 @@ int vlg_warp_bwd_src(const vlg_problem_t *prob, const float *coords, void *d_src
     pp.far_acc = L.far_acc ? (long long *)(ws + L.far_acc) : nullptr;
     pp.far_list = L.far_list ? (const int4 *)(ws + L.far_list) : nullptr;
     pp.tile_flags = (const uint32_t *)(ws + L.tile_flags);
+    pp.seg_cnt = (prob->flags & VLG_FLAG_FAR_WIDE) ? nullptr : (const uint32_t *)(ws + L.seg_cnt);
     pp.flagged_list = (const int *)(ws + L.flagged);
     pp.hdr = (WsHeader *)(ws + L.header);
     pp.tile_disp = (const float *)(ws + L.tile_disp);

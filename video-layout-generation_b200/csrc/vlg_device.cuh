@@ -19,7 +19,7 @@ namespace vlg {
 struct WsHeader {
     uint32_t status;        // VLG_STATUS_* bits (sticky until the next pass-1 launch)
     uint32_t maxdisp_bits;  // float bits of max |displacement| (non-negative => uint order == float order)
-    uint32_t maxgrad_bits;  // float bits of max |d_out| (scale of the fixed-point far path)
+    uint32_t reserved0;
     uint32_t far_count;     // number of far output pixels
     unsigned long long n_valid;  // labels != ignore_index
     uint32_t blocks_done;   // pass-1 CTAs that have published their partial sums (last one reduces)
@@ -29,7 +29,8 @@ struct WsHeader {
     double ce_denom;        // divisor of the weighted CE sum: sum_k w_k * hist_k (VLG_CE_NORM_TORCH with weights)
     uint32_t n_tile;        // partial rows written by the tile kernel (pass1_kernel), 0: it did not run
     uint32_t n_lay;         // per-CTA partial rows written by lay_tile_kernel
-    uint32_t pad[2];
+    uint32_t maxgrad_rgb_bits;  // float bits of max |d_out| over the rgb channels    } scales of the fixed-point far path, which treats
+    uint32_t maxgrad_lay_bits;  // ... over the layout channels                       } the two groups separately (vlg_pass2.cuh)
     unsigned long long prof[8];   // spare (tuning builds: per-section cycle counters)
     unsigned long long hist[32];  // labels per class (only filled when class weights are given)
 };
@@ -112,7 +113,7 @@ __host__ __device__ __forceinline__ int64_t dout_index(int64_t n, int64_t HW, in
 }
 
 struct WsLayout {
-    size_t header, tile_flags, tile_disp, partials, partials_rgb, partials_lay, flagged, dout_rgb, dout_lay, far_acc, far_list, total;
+    size_t header, tile_flags, tile_disp, seg_cnt, partials, partials_rgb, partials_lay, flagged, dout_rgb, dout_lay, far_acc, far_list, total;
     size_t rec_code, rec_frac;   // tap records of pass 1 for pass 2 (pitched rows)
     int64_t n_blocks;
     int64_t pitch;               // row pitch (pixels) of dout_rgb / rec_code / rec_frac: W rounded up to 4, so that every
@@ -128,6 +129,35 @@ constexpr int kThreads = kTW * kTH;
 
 __host__ __device__ inline int64_t tiles_x(int64_t W) { return (W + kTW - 1) / kTW; }
 __host__ __device__ inline int64_t tiles_y(int64_t H) { return (H + kTH - 1) / kTH; }
+
+// A far output pixel (vlg_pass2.cuh) announces itself to the source tiles its four taps (x0 | x0+1, y0 | y0+1) land in: the
+// tile is flagged (once: an L2 load first, the returning atomic only while the flag still reads 0 -- with rough flow every
+// tile is hit hundreds of times) and the row of the tile counts one more far pixel (a RED, no round trip).  The two taps
+// of a row share a segment unless they straddle a tile border.
+__device__ __forceinline__ void far_announce(uint32_t *tile_flags, int *flagged_list, uint32_t *seg_cnt, WsHeader *hdr,
+                                             int n, int tiles_x_, int tiles_y_, int x0, int y0, int W, int H) {
+    int flagged = -1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int yy = y0 + r;
+        if (yy < 0 || yy >= H) continue;
+        int last = -1;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int xx = x0 + c;
+            if (xx < 0 || xx >= W) continue;
+            const int tl = (n * tiles_y_ + yy / kTH) * tiles_x_ + xx / kTW;
+            if (tl == last) continue;
+            last = tl;
+            if (seg_cnt) atomicAdd(&seg_cnt[(int64_t)tl * kTH + (yy & (kTH - 1))], 1u);
+            if (tl != flagged) {
+                flagged = tl;
+                if (__ldcg(&tile_flags[tl]) == 0u && atomicOr(&tile_flags[tl], 1u) == 0u)
+                    flagged_list[atomicAdd(&hdr->n_flagged, 1u)] = tl;
+            }
+        }
+    }
+}
 
 // ---------------------------------------------------------------- typed loads / stores
 template <typename T> __device__ __forceinline__ float to_f(T v);

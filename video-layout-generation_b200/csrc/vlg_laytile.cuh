@@ -76,6 +76,7 @@ struct LayParams {
     float *tile_disp;              // [n_tiles] max NEAR displacement per 32x8 tile (zero-initialised, atomicMax)
     int4 *far_list;                // queue of far output pixels (see Pass2Params::far_list)
     uint32_t *tile_flags;
+    uint32_t *seg_cnt;             // [n_tiles][kTH] far output pixels per row of a SOURCE tile (zeroed with the header)
     int *flagged_list;
     ReduceParams red;
     WsHeader *hdr;
@@ -276,22 +277,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
             if (p.far_list) {
                 p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = make_int4((int)(img + (int64_t)y * W + x), (tp.x0 + 8) | ((tp.y0 + 8) << 16),
                                                                           __float_as_int(tp.ix - tp.fx0), __float_as_int(tp.iy - tp.fy0));
-                // flag the source tiles its taps land in.  The four taps share one tile unless they straddle a tile border, and a
-                // tile is flagged once: an L2 load first, the atomic only while the flag still reads 0 (with rough flow every tile
-                // is hit hundreds of times -- 24 M returning atomics on 29 K words in BASELINE config 5).
-                int last = -1;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const int xx = tp.x0 + (k4 & 1), yy = tp.y0 + (k4 >> 1);
-                    if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-                        const int tl = (g.n * tiles_y + yy / kTH) * tiles_x + xx / kTW;
-                        if (tl != last) {
-                            last = tl;
-                            if (__ldcg(&p.tile_flags[tl]) == 0u && atomicOr(&p.tile_flags[tl], 1u) == 0u)
-                                p.flagged_list[atomicAdd(&p.hdr->n_flagged, 1u)] = tl;
-                        }
-                    }
-                }
+                far_announce(p.tile_flags, p.flagged_list, p.seg_cnt, p.hdr, g.n, tiles_x, tiles_y, tp.x0, tp.y0, W, H);
             } else {
                 atomicOr(&p.hdr->status, VLG_STATUS_FAR_TAPS);
             }
@@ -465,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
     if (lane == 0) {
         sm.red[wid][0] = s_ce; sm.red[wid][1] = s_tvh; sm.red[wid][2] = s_tvw;
         if (m_disp > 0.f) atomicMax(&p.hdr->maxdisp_bits, __float_as_uint(m_disp));
-        if (m_grad > 0.f) atomicMax(&p.hdr->maxgrad_bits, __float_as_uint(m_grad));
+        if (m_grad > 0.f) atomicMax(&p.hdr->maxgrad_lay_bits, __float_as_uint(m_grad));
     }
     __syncthreads();
     if (tid == 0) {

@@ -54,6 +54,7 @@ struct Pass1Params {
     float *partials;        // [n_blocks][kPartialSlots]
     float *tile_disp;       // [n_blocks] max displacement among the tile's NEAR output pixels (WARP)
     int4 *far_list;         // [P] queue of FAR output pixels: {pixel index, tap cell, fractional weights} (nullable: no source gradient / no far path)
+    uint32_t *seg_cnt;      // [n_blocks][kTH] far output pixels per row of a SOURCE tile (zeroed with the header)
     uint32_t *tile_flags;   // [n_blocks] != 0 where a far pixel lands in that SOURCE tile (zeroed with the header)
     int *flagged_list;      // [n_blocks] compacted ids of the flagged source tiles
     ReduceParams red;       // red.out != NULL: the last CTA also performs the final reduction
@@ -523,15 +524,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                 if (p.far_list) {
                     p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = make_int4((int)(img_px + o), (t.x0 + 8) | ((t.y0 + 8) << 16),
                                                                               __float_as_int(t.ix - t.fx0), __float_as_int(t.iy - t.fy0));
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const int xx = t.x0 + (k4 & 1), yy = t.y0 + (k4 >> 1);
-                        if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-                            const int tl = (n * p.tiles_y + yy / kTH) * p.tiles_x + xx / kTW;
-                            if (atomicOr(&p.tile_flags[tl], 1u) == 0u)
-                                p.flagged_list[atomicAdd(&p.hdr->n_flagged, 1u)] = tl;
-                        }
-                    }
+                    far_announce(p.tile_flags, p.flagged_list, p.seg_cnt, p.hdr, n, p.tiles_x, p.tiles_y, t.x0, t.y0, W, H);
                 } else {
                     atomicOr(&p.hdr->status, VLG_STATUS_FAR_TAPS);
                 }
@@ -785,7 +778,10 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
         }
         if (WARP && p.tile_disp) p.tile_disp[bt] = nr;
         if (d > 0.f) atomicMax(&p.hdr->maxdisp_bits, __float_as_uint(d));
-        if (g > 0.f) atomicMax(&p.hdr->maxgrad_bits, __float_as_uint(g));
+        if (g > 0.f) {   // this organisation keeps one maximum over all channels: a valid (looser) bound for either group
+            atomicMax(&p.hdr->maxgrad_rgb_bits, __float_as_uint(g));
+            atomicMax(&p.hdr->maxgrad_lay_bits, __float_as_uint(g));
+        }
     }
 
     // ---------------- phase 4: the last CTA to finish reduces all partial rows ----------------

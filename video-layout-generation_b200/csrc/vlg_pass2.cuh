@@ -33,6 +33,7 @@ struct Pass2Params {
     long long *far_acc;       // [P][3+K] fixed point, nullable (VLG_FLAG_NO_FAR_PATH)
     const int4 *far_list;     // [far_count] far output pixels queued by pass 1: {pixel index, (x0 + 8) | (y0 + 8) << 16, bits of ix - x0, bits of iy - y0}
     const uint32_t *tile_flags;  // [n_blocks] source tiles that receive far contributions
+    const uint32_t *seg_cnt;     // [n_blocks][kTH] far output pixels with a tap in that row of that source tile (pass 1 counted them)
     const int *flagged_list;  // [n_flagged] ids of those tiles
     const float *tile_disp;   // [n_blocks] per-tile max NEAR displacement written by pass 1
     WsHeader *hdr;
@@ -60,13 +61,75 @@ __device__ __forceinline__ int near_radius(const Pass2Params &p, int n, int tyi,
 
 // 2^e such that (sum of <= H*W contributions of magnitude <= maxgrad) * 2^e < 2^62
 __device__ __forceinline__ int far_scale_exp(const WsHeader *hdr, int64_t HW) {
-    const float g = __uint_as_float(hdr->maxgrad_bits);
+    const float g = __uint_as_float(max(hdr->maxgrad_rgb_bits, hdr->maxgrad_lay_bits));   // non-negative floats order like their bits
     int eg = 0, ehw = 0;
     frexpf(fmaxf(g, 1e-37f), &eg);
     frexp((double)HW, &ehw);
     return min(61 - eg - ehw, 96);   // capped so that 2^e is an fp32 number too (gradients below 2^-96 are noise anyway)
 }
 __device__ __forceinline__ double far_scale(const WsHeader *hdr, int64_t HW) { return ldexp(1.0, far_scale_exp(hdr, HW)); }
+
+// Packed far accumulators.  The scatter is bound by the 32-byte sectors the L2 atomic units process (measured: 286 G
+// lane-operations/s for runs of 64-bit REDs, whatever the SMs do), so the unit that halves its time is the sector:
+// two channels share one 64-bit word, V = (a1 << 32) + a0 with a = round(v * 2^e) as SIGNED 32-bit integers, added as one
+// signed 64-bit integer.  Sums of V are exact; the low lane is read back as a signed 32-bit integer and subtracted
+// before the high lane is taken, which undoes every borrow.  What makes 32 bits enough is a bound on the NUMBER of
+// contributions: pass 1 counts, per row of every source tile (a "segment": 32 source pixels), the far output pixels
+// that have a tap in it (`seg_cnt`) -- an output pixel adds at most one tap to a given source pixel, so no source pixel
+// of the segment receives more than cnt contributions.  With h = ceil(log2 cnt), eg = the exponent of the largest
+// |d_out| of the channel's group (rgb and layout gradients differ by orders of magnitude: two maxima) and
+// e = 30 - h - eg, no lane can leave (-2^31, 2^31), and every contribution is rounded at 2^-(30-h) of the group's
+// largest gradient: h <= 6 for any flow that is not compressive, i.e. 24 bits -- fp32's own resolution.
+// Segments with more than kFarPackedMaxCnt pixels (strongly compressive flow) keep one 64-bit accumulator per
+// channel, as does any K whose channel pairs do not fit 32 lanes.  The mode is a function of the integer count only,
+// and integer adds are associative: the result does not depend on the order of the atomics in either mode.
+// Storage: a segment owns npx * (3 + K) words of `far_acc` either way; the packed mode uses the first npx * PW of them.
+constexpr unsigned kFarPackedMaxCnt = 512;
+template <int K> struct FarPack {
+    static constexpr int CH = 3 + K, PW = (CH + 1) / 2;
+    static constexpr bool can = 2 * PW <= 32;
+};
+__device__ __forceinline__ int float_exp(uint32_t bits) {
+    int eg = 0;
+    frexpf(fmaxf(__uint_as_float(bits), 1e-37f), &eg);
+    return eg;
+}
+__device__ __forceinline__ int ceil_log2(unsigned cnt) { return cnt > 1u ? 32 - __clz((int)(cnt - 1u)) : 0; }
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((min(max(e, -126), 127) + 127) << 23); }
+// exponent of the packed fixed point of a group (eg) in a segment that receives cnt far pixels
+__device__ __forceinline__ int far_packed_exp(int eg, unsigned cnt) { return min(30 - ceil_log2(cnt) - eg, 96); }
+template <int K> __device__ __forceinline__ bool far_seg_packed(unsigned cnt) { return FarPack<K>::can && cnt <= kFarPackedMaxCnt; }
+// far pixels counted in segment `seg` (no counts -- VLG_FLAG_FAR_WIDE -- reads as "too many": the wide mode)
+__device__ __forceinline__ unsigned far_seg_count(const uint32_t *seg_cnt, int64_t seg) { return seg_cnt ? __ldg(seg_cnt + seg) : 0xFFFFFFFFu; }
+
+// adds the far sums of source pixel (n, sy, sx) of tile bt (whose first column is tx0) to acc_r / acc_l
+template <int K>
+__device__ __forceinline__ void far_read(const Pass2Params &p, int n, int bt, int sy, int sx, int tx0, float (&acc_r)[3], float (&acc_l)[K]) {
+    constexpr int CH = FarPack<K>::CH, PW = FarPack<K>::PW;
+    const unsigned cnt = far_seg_count(p.seg_cnt, (int64_t)bt * kTH + (sy & (kTH - 1)));
+    const long long *seg = p.far_acc + ((int64_t)n * p.HW + (int64_t)sy * p.cc.W + tx0) * CH;
+    if (far_seg_packed<K>(cnt)) {
+        const float inv_r = pow2f(-far_packed_exp(float_exp(p.hdr->maxgrad_rgb_bits), cnt));
+        const float inv_l = pow2f(-far_packed_exp(float_exp(p.hdr->maxgrad_lay_bits), cnt));
+        const long long *fa = seg + (sx - tx0) * PW;
+#pragma unroll
+        for (int w = 0; w < PW; ++w) {
+            const long long S = fa[w];
+            const int lo = (int)(unsigned)((unsigned long long)S & 0xFFFFFFFFull);
+            const int hi = (int)((S - (long long)lo) >> 32);
+            const int c0 = 2 * w, c1 = 2 * w + 1;
+            if (c0 < 3) acc_r[c0] += (float)lo * inv_r; else acc_l[c0 - 3] += (float)lo * inv_l;
+            if (c1 < CH) { if (c1 < 3) acc_r[c1] += (float)hi * inv_r; else acc_l[c1 - 3] += (float)hi * inv_l; }
+        }
+    } else {
+        const double inv = 1.0 / far_scale(p.hdr, p.HW);
+        const long long *fa = seg + (sx - tx0) * CH;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc_r[c] += (float)((double)fa[c] * inv);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc_l[k] += (float)((double)fa[3 + k] * inv);
+    }
+}
 
 template <int K>
 constexpr size_t pass2_smem_bytes() {
@@ -217,14 +280,7 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_kernel(const Pass2Params p,
         }
     }
     const int64_t so = img_px + (int64_t)sy * W + sx;
-    if (live && tile_far) {
-        const double inv = 1.0 / far_scale(p.hdr, p.HW);
-        const long long *fa = p.far_acc + so * (3 + K);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc_r[c] += (float)((double)fa[c] * inv);
-#pragma unroll
-        for (int k = 0; k < K; ++k) acc_l[k] += (float)((double)fa[3 + k] * inv);
-    }
+    if (live && tile_far) far_read<K>(p, n, bt, sy, sx, tx0, acc_r, acc_l);
     if (live && want_rgb) store_px<T, 3>(reinterpret_cast<T *>(p.d_src_rgb) + so * 3, acc_r);
     if (want_lay) {
         // A thread-per-pixel store of 80-byte pixels costs 20 L1 wavefronts per 128-bit store
@@ -358,14 +414,7 @@ __global__ void __launch_bounds__(kThreads, 4) pass2_rec_kernel(const Pass2Param
         }
     }
     const int64_t so = img_px + (int64_t)sy * W + sx;
-    if (live && tile_far) {
-        const double inv = 1.0 / far_scale(p.hdr, p.HW);
-        const long long *fa = p.far_acc + so * (3 + K);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc_r[c] += (float)((double)fa[c] * inv);
-#pragma unroll
-        for (int k = 0; k < K; ++k) acc_l[k] += (float)((double)fa[3 + k] * inv);
-    }
+    if (live && tile_far) far_read<K>(p, n, bt, sy, sx, tx0, acc_r, acc_l);
     if (live && want_rgb) store_px<T, 3>(reinterpret_cast<T *>(p.d_src_rgb) + so * 3, acc_r);
     if (want_lay) {
         // transpose through shared memory: each warp writes its tile row (32 px x K, contiguous in HBM)
@@ -421,7 +470,8 @@ __global__ void __launch_bounds__(kThreads) far_zero_kernel(const Pass2Params p)
         const int n = t / (p.tiles_y * p.tiles_x), rem = t - n * (p.tiles_y * p.tiles_x);
         const int y = (rem / p.tiles_x) * kTH + wid, x0 = (rem % p.tiles_x) * kTW;
         if (y >= p.cc.H) continue;
-        const int words = min(kTW, p.cc.W - x0) * (3 + K);
+        const int wpp = far_seg_packed<K>(far_seg_count(p.seg_cnt, (int64_t)t * kTH + wid)) ? FarPack<K>::PW : 3 + K;   // words per pixel
+        const int words = min(kTW, p.cc.W - x0) * wpp;
         long long *a = p.far_acc + ((int64_t)n * p.HW + (int64_t)y * p.cc.W + x0) * (3 + K);
         for (int q = lane; q < words; q += 32) a[q] = 0;
     }
@@ -436,44 +486,149 @@ __global__ void __launch_bounds__(kThreads) far_zero_kernel(const Pass2Params p)
 // (First version: one THREAD per contribution, ~400 instructions of index arithmetic each: 11.6 ms for the 6 M
 // far pixels of BASELINE config 5.  Second: one warp per pixel, lanes = (tap, channel) pairs, taps re-derived by
 // make_taps, fp64 scaling: 273 instructions per pixel, 2.56 ms.)
+// One far pixel's four taps, by the whole warp.  `modes`: 5 bits per (row, side) segment -- bit 0 = packed, bits 1-4 = h.
 template <int K>
-__global__ void __launch_bounds__(kThreads) far_scatter_kernel(const Pass2Params p) {
+__device__ __forceinline__ void far_scatter_one(const Pass2Params &p, unsigned lane, int wd, int side_of_lane, int eg0, int eg1, float scale,
+                                                unsigned n, int x0, int y0, float fx, float fy, unsigned modes,
+                                                const float (&d)[(3 + K + 31) / 32], float d0, float d1) {
+    constexpr int CH = FarPack<K>::CH, PW = FarPack<K>::PW;
+    const int H = p.cc.H, W = p.cc.W;
+    // east/south = frac, west/north = 1 - frac: the weights of the near path (pass2_rec_kernel), bit-identical to the
+    // forward's for every in-image tap
+    const float wx[2] = {__fsub_rn(1.0f, fx), fx}, wy[2] = {__fsub_rn(1.0f, fy), fy};
+    long long *img_acc = p.far_acc + (int64_t)n * p.HW * CH;
+    const bool okw = x0 >= 0 && x0 < W, oke = x0 + 1 >= 0 && x0 + 1 < W;
+    const int txw = x0 >> 5, txe = (x0 + 1) >> 5;                           // kTW == 32
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int ys = y0 + r;
+        if (ys < 0 || ys >= H) continue;                                    // warp-uniform
+        const unsigned mw = (modes >> (10 * r)) & 31u, me = (modes >> (10 * r + 5)) & 31u;
+        long long *row_acc = img_acc + (int64_t)ys * W * CH;
+        if (okw && oke && txw == txe && (mw & 1u)) {
+            // both taps of the row in one packed segment: one run of 2 PW consecutive words
+            if ((int)lane < 2 * PW) {
+                const int h = (int)(mw >> 1);
+                const float wt = __fmul_rn(wx[side_of_lane], wy[r]);
+                const long long a0 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d0), pow2f(min(30 - h - eg0, 96))));
+                const long long a1 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d1), pow2f(min(30 - h - eg1, 96))));
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(row_acc + (int64_t)(txw * kTW) * CH + (x0 - txw * kTW) * PW + lane);
+                atomicAdd(dst, (unsigned long long)(a1 * 4294967296ll + a0));
+            }
+            continue;
+        }
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!(sd ? oke : okw)) continue;
+            const unsigned m = sd ? me : mw;
+            const int xs = x0 + sd, tx0s = (sd ? txe : txw) * kTW;
+            const float wt = __fmul_rn(wx[sd], wy[r]);
+            long long *seg = row_acc + (int64_t)tx0s * CH;
+            if (m & 1u) {
+                if ((int)lane < PW) {
+                    const int h = (int)(m >> 1);
+                    const long long a0 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d0), pow2f(min(30 - h - eg0, 96))));
+                    const long long a1 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d1), pow2f(min(30 - h - eg1, 96))));
+                    atomicAdd(reinterpret_cast<unsigned long long *>(seg + (xs - tx0s) * PW + lane), (unsigned long long)(a1 * 4294967296ll + a0));
+                }
+            } else {
+#pragma unroll
+                for (int c0 = 0; c0 < CH; c0 += 32) {
+                    const int c = c0 + (int)lane;
+                    if (c < CH)
+                        atomicAdd(reinterpret_cast<unsigned long long *>(seg + (xs - tx0s) * CH + c),
+                                  (unsigned long long)__float2ll_rn(__fmul_rn(__fmul_rn(wt, d[c0 / 32]), scale)));
+                }
+            }
+        }
+    }
+}
+
+// The kernel is a chain of dependent memory round trips per far pixel (queue entry -> segment counts -> d_out), not a
+// stream: with one pixel per warp iteration it ran at the speed of that chain (2.4 ms for the 6 M far pixels of BASELINE
+// config 5, whatever the atomics cost).  So a warp takes 32 queue entries at a time, ONE PER LANE (entry, index
+// arithmetic and the four segment counts are loaded / computed lane-parallel: 32 chains in flight), and then walks them
+// VLG_FAR_U at a time: their d_out loads are issued before the first of them is consumed.
+#ifndef VLG_FAR_U
+#define VLG_FAR_U 2         // pixels whose d_out loads are in flight together.  Measured on BASELINE config 5 (U / CTAs per SM):
+#endif                      // 2/4 1.33 ms, 2/5 1.42 (spills), 4/3 1.52, 4/4 1.56 (spills), 8/3 1.55, 8/2 2.11 -- warps beat depth
+#ifndef VLG_FAR_CTAS
+#define VLG_FAR_CTAS 4      // 62 registers
+#endif
+template <int K>
+__global__ void __launch_bounds__(kThreads, VLG_FAR_CTAS) far_scatter_kernel(const Pass2Params p) {
     const unsigned n_far = p.hdr->far_count;
     if (n_far == 0) return;
     const int H = p.cc.H, W = p.cc.W;
-    constexpr int CH = 3 + K;
-    static_assert(CH <= 32 || CH <= 64, "channels are walked in at most two lane rounds");
+    constexpr int CH = FarPack<K>::CH, PW = FarPack<K>::PW, U = VLG_FAR_U, ND = (CH + 31) / 32;
+    static_assert(CH <= 64, "channels are walked in at most two lane rounds");
     const float scale = ldexpf(1.0f, far_scale_exp(p.hdr, p.HW));    // a power of two: v * scale is exact in fp32
     const unsigned lane = threadIdx.x & 31;
+    // packed segments: lanes 0 .. 2 PW - 1 = (west | east tap, word); a lane adds channels 2 wd and 2 wd + 1 with one atomic
+    const int wd = (int)lane % PW, side_of_lane = (int)lane / PW;
+    const int eg0 = float_exp(2 * wd < 3 ? p.hdr->maxgrad_rgb_bits : p.hdr->maxgrad_lay_bits);
+    const int eg1 = float_exp(2 * wd + 1 < 3 ? p.hdr->maxgrad_rgb_bits : p.hdr->maxgrad_lay_bits);
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned HWu = (unsigned)p.HW;
-    for (unsigned j = gw; j < n_far; j += nw) {
-        const int4 e = __ldg(p.far_list + j);
-        const unsigned i = (unsigned)e.x;                    // pixel index < 2^31 (check_problem)
-        const unsigned n = i / HWu, rem = i - n * HWu;
-        const int y = (int)(rem / (unsigned)W), x = (int)(rem - (unsigned)y * (unsigned)W);
-        const int x0 = (int)((unsigned)e.y & 0xFFFFu) - 8, y0 = (int)((unsigned)e.y >> 16) - 8;
-        const float fx = __int_as_float(e.z), fy = __int_as_float(e.w);
-        // east/south = frac, west/north = 1 - frac: the weights of the near path (pass2_rec_kernel), bit-identical to the
-        // forward's for every in-image tap
-        const float wx[2] = {__fsub_rn(1.0f, fx), fx}, wy[2] = {__fsub_rn(1.0f, fy), fy};
-        const float *drgb = p.d_out_rgb ? p.d_out_rgb + (((int64_t)n * H + y) * p.pitch + x) * 3 : nullptr;
-        const float *dlay = p.d_out_lay ? p.d_out_lay + (int64_t)i * K : nullptr;
-        long long *img_acc = p.far_acc + (int64_t)n * p.HW * CH;
+    // a short queue (a handful of far pixels in an otherwise smooth flow) is spread over all warps instead of being
+    // walked by a few of them: `per` entries per warp and round
+    const unsigned per = min(32u, max(1u, (n_far + nw - 1u) / nw));
+    for (unsigned base = gw * per; base < n_far; base += nw * per) {
+        // ---- lane-parallel: one queue entry per lane ----
+        const unsigned j = lane < per ? base + lane : n_far;
+        const int4 e = j < n_far ? __ldg(p.far_list + j) : make_int4(0, 8 | (8 << 16), 0, 0);
+        const unsigned my_i = (unsigned)e.x;                 // pixel index < 2^31 (check_problem)
+        const unsigned my_n = my_i / HWu, rem = my_i - my_n * HWu;
+        const unsigned my_y = rem / (unsigned)W, my_x = rem - my_y * (unsigned)W;
+        const unsigned my_q = (my_n * (unsigned)H + my_y) * (unsigned)p.pitch + my_x;     // pitched pixel index (< 2^32)
+        const int my_x0 = (int)((unsigned)e.y & 0xFFFFu) - 8, my_y0 = (int)((unsigned)e.y >> 16) - 8;
+        unsigned my_modes = 0u;
+        {
+            const bool okw = my_x0 >= 0 && my_x0 < W, oke = my_x0 + 1 >= 0 && my_x0 + 1 < W;
+            const int txw = my_x0 >> 5, txe = (my_x0 + 1) >> 5;
+            unsigned cnt[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int c0 = 0; c0 < CH; c0 += 32) {
-            const int c = c0 + (int)lane;
-            const float *src = c < 3 ? drgb : dlay;
-            float d = 0.f;
-            const bool have = c < CH && src != nullptr;
-            if (have) d = __ldg(src + (c < 3 ? c : c - 3));
+            for (int r = 0; r < 2; ++r) {
+                const int ys = my_y0 + r;
+                if (ys < 0 || ys >= H || j >= n_far) continue;
+                const int64_t seg_row = ((int64_t)my_n * p.tiles_y + ys / kTH) * p.tiles_x * kTH + (ys & (kTH - 1));
+                if (okw) cnt[2 * r] = far_seg_count(p.seg_cnt, seg_row + (int64_t)txw * kTH);
+                if (oke) cnt[2 * r + 1] = (okw && txe == txw) ? cnt[2 * r] : far_seg_count(p.seg_cnt, seg_row + (int64_t)txe * kTH);
+            }
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                const int xs = x0 + (k4 & 1), ys = y0 + (k4 >> 1);
-                if (xs < 0 || xs >= W || ys < 0 || ys >= H || !have) continue;      // warp-uniform but for `have`
-                const float wt = __fmul_rn(wx[k4 & 1], wy[k4 >> 1]);
-                unsigned long long *dst = reinterpret_cast<unsigned long long *>(img_acc + ((int64_t)ys * W + xs) * CH + c);
-                atomicAdd(dst, (unsigned long long)__float2ll_rn(__fmul_rn(__fmul_rn(wt, d), scale)));
+            for (int q = 0; q < 4; ++q)
+                if (far_seg_packed<K>(cnt[q])) my_modes |= (1u | ((unsigned)ceil_log2(cnt[q]) << 1)) << (5 * q);
+        }
+        const int nb = (int)min(per, n_far - base);
+        for (int k0 = 0; k0 < nb; k0 += U) {
+            unsigned fn[U], fmodes[U]; int fx0[U], fy0[U]; float ffx[U], ffy[U], d[U][ND], d0[U], d1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int sl = min(k0 + u, 31);
+                const unsigned i = __shfl_sync(0xffffffffu, my_i, sl), q = __shfl_sync(0xffffffffu, my_q, sl);
+                fn[u] = __shfl_sync(0xffffffffu, my_n, sl);
+                fx0[u] = __shfl_sync(0xffffffffu, my_x0, sl); fy0[u] = __shfl_sync(0xffffffffu, my_y0, sl);
+                ffx[u] = __int_as_float(__shfl_sync(0xffffffffu, e.z, sl)); ffy[u] = __int_as_float(__shfl_sync(0xffffffffu, e.w, sl));
+                fmodes[u] = __shfl_sync(0xffffffffu, my_modes, sl);
+                const float *drgb = p.d_out_rgb ? p.d_out_rgb + (int64_t)q * 3 : nullptr;
+                const float *dlay = p.d_out_lay ? p.d_out_lay + (int64_t)i * K : nullptr;
+#pragma unroll
+                for (int c0 = 0; c0 < CH; c0 += 32) {
+                    const int c = c0 + (int)lane;
+                    const float *src = c < 3 ? drgb : dlay;
+                    d[u][c0 / 32] = (c < CH && src != nullptr && k0 + u < nb) ? __ldg(src + (c < 3 ? c : c - 3)) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                d0[u] = d1[u] = 0.f;
+                if (FarPack<K>::can) {
+                    d0[u] = __shfl_sync(0xffffffffu, d[u][0], 2 * wd);
+                    d1[u] = __shfl_sync(0xffffffffu, d[u][0], (2 * wd + 1) & 31);
+                    if (2 * wd + 1 >= CH) d1[u] = 0.f;
+                }
+                if (k0 + u < nb)                                                      // warp-uniform
+                    far_scatter_one<K>(p, lane, wd, side_of_lane, eg0, eg1, scale, fn[u], fx0[u], fy0[u], ffx[u], ffy[u], fmodes[u], d[u], d0[u], d1[u]);
             }
         }
     }

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kRgbThreads, VLG_RGB_MIN_BLOCKS) rgb_strip_ker
         o.w = __uint_as_float(prof_stamp());     // where and when this warp finished
 #endif
         reinterpret_cast<float4 *>(p.partials)[gw] = o;
-        if (m_grad > 0.f) atomicMax(&p.hdr->maxgrad_bits, __float_as_uint(m_grad));
+        if (m_grad > 0.f) atomicMax(&p.hdr->maxgrad_rgb_bits, __float_as_uint(m_grad));
         if (gw == 0) p.hdr->n_rgb = gridDim.x * (kRgbThreads / 32);
     }
 

@@ -44,6 +44,8 @@ class WarpLossConfig:
                                           # 'tile' first tile kernel
     pass2_records: bool = True            # pass 2 gathers from the tap records pass 1 wrote (all staging by TMA);
                                           # False: it re-derives them from the coordinates (first pass-2 kernel)
+    far_packed: bool = True               # far path packs two 32-bit lanes per 64-bit atomic where the far-pixel count of a source-tile row allows
+                                          # (False: always one 64-bit accumulator per channel)
     term_mask: int = 0                    # 0 = all terms
     class_weight: Optional[torch.Tensor] = None   # per-class CE weights (K floats on the device)
     ce_norm: str = "torch"                # 'torch' (weighted mean) | 'count' (sum / n_known, src/models/simple.py:56-59)
@@ -132,6 +134,8 @@ def _problem(N, H, W, K, dtype, cfg: WarpLossConfig) -> Problem:
         flags |= _cabi.FLAG_TILE_RGB | _cabi.FLAG_TILE_LAYOUT
     if not cfg.pass2_records:
         flags |= _cabi.FLAG_PASS2_COORDS
+    if not cfg.far_packed:
+        flags |= _cabi.FLAG_FAR_WIDE
     if cfg.layout_kernel not in ("tile2", "tile"):
         raise VlgError(f"layout_kernel must be 'tile2' or 'tile', not {cfg.layout_kernel!r}")
     flags |= {"tile2": 0, "tile": _cabi.FLAG_TILE_LAYOUT}[cfg.layout_kernel]
