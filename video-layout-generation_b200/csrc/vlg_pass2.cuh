@@ -78,7 +78,7 @@ __device__ __forceinline__ double far_scale(const WsHeader *hdr, int64_t HW) { r
 // that have a tap in it (`seg_cnt`) -- an output pixel adds at most one tap to a given source pixel, so no source pixel
 // of the segment receives more than cnt contributions.  With h = ceil(log2 cnt), eg = the exponent of the largest
 // |d_out| of the channel's group (rgb and layout gradients differ by orders of magnitude: two maxima) and
-// e = 30 - h - eg, no lane can leave (-2^31, 2^31), and every contribution is rounded at 2^-(30-h) of the group's
+// e = 30 - eg - h, no lane can leave (-2^31, 2^31), and every contribution is rounded at 2^-(30-h) of the group's
 // largest gradient: h <= 6 for any flow that is not compressive, i.e. 24 bits -- fp32's own resolution.
 // Segments with more than kFarPackedMaxCnt pixels (strongly compressive flow) keep one 64-bit accumulator per
 // channel, as does any K whose channel pairs do not fit 32 lanes.  The mode is a function of the integer count only,
@@ -97,7 +97,7 @@ __device__ __forceinline__ int float_exp(uint32_t bits) {
 __device__ __forceinline__ int ceil_log2(unsigned cnt) { return cnt > 1u ? 32 - __clz((int)(cnt - 1u)) : 0; }
 __device__ __forceinline__ float pow2f(int e) { return __int_as_float((min(max(e, -126), 127) + 127) << 23); }
 // exponent of the packed fixed point of a group (eg) in a segment that receives cnt far pixels
-__device__ __forceinline__ int far_packed_exp(int eg, unsigned cnt) { return min(30 - ceil_log2(cnt) - eg, 96); }
+__device__ __forceinline__ int far_packed_exp(int eg, unsigned cnt) { return min(30 - eg, 96) - ceil_log2(cnt); }
 template <int K> __device__ __forceinline__ bool far_seg_packed(unsigned cnt) { return FarPack<K>::can && cnt <= kFarPackedMaxCnt; }
 // far pixels counted in segment `seg` (no counts -- VLG_FLAG_FAR_WIDE -- reads as "too many": the wide mode)
 __device__ __forceinline__ unsigned far_seg_count(const uint32_t *seg_cnt, int64_t seg) { return seg_cnt ? __ldg(seg_cnt + seg) : 0xFFFFFFFFu; }
@@ -510,8 +510,8 @@ __device__ __forceinline__ void far_scatter_one(const Pass2Params &p, unsigned l
             if ((int)lane < 2 * PW) {
                 const int h = (int)(mw >> 1);
                 const float wt = __fmul_rn(wx[side_of_lane], wy[r]);
-                const long long a0 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d0), pow2f(min(30 - h - eg0, 96))));
-                const long long a1 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d1), pow2f(min(30 - h - eg1, 96))));
+                const long long a0 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d0), pow2f(min(30 - eg0, 96) - h)));
+                const long long a1 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d1), pow2f(min(30 - eg1, 96) - h)));
                 unsigned long long *dst = reinterpret_cast<unsigned long long *>(row_acc + (int64_t)(txw * kTW) * CH + (x0 - txw * kTW) * PW + lane);
                 atomicAdd(dst, (unsigned long long)(a1 * 4294967296ll + a0));
             }
@@ -527,8 +527,8 @@ __device__ __forceinline__ void far_scatter_one(const Pass2Params &p, unsigned l
             if (m & 1u) {
                 if ((int)lane < PW) {
                     const int h = (int)(m >> 1);
-                    const long long a0 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d0), pow2f(min(30 - h - eg0, 96))));
-                    const long long a1 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d1), pow2f(min(30 - h - eg1, 96))));
+                    const long long a0 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d0), pow2f(min(30 - eg0, 96) - h)));
+                    const long long a1 = (long long)__float2int_rn(__fmul_rn(__fmul_rn(wt, d1), pow2f(min(30 - eg1, 96) - h)));
                     atomicAdd(reinterpret_cast<unsigned long long *>(seg + (xs - tx0s) * PW + lane), (unsigned long long)(a1 * 4294967296ll + a0));
                 }
             } else {
@@ -570,6 +570,14 @@ __global__ void __launch_bounds__(kThreads, VLG_FAR_CTAS) far_scatter_kernel(con
     const int eg1 = float_exp(2 * wd + 1 < 3 ? p.hdr->maxgrad_rgb_bits : p.hdr->maxgrad_lay_bits);
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned HWu = (unsigned)p.HW;
+    const float S0 = pow2f(min(30 - eg0, 96)), S1 = pow2f(min(30 - eg1, 96));     // this lane's two channels: 2^(30 - eg) ...
+    // where this lane finds its two channels of a pixel's d_out: base + pixel index * stride (rgb staging: pitched index q,
+    // 12-byte pixels; layout staging: index i, K floats)
+    const int c0 = 2 * wd, c1 = 2 * wd + 1;
+    const bool has0 = (int)lane < 2 * PW && (c0 >= 3 || p.d_out_rgb != nullptr), has1 = (int)lane < 2 * PW && c1 < CH && (c1 >= 3 || p.d_out_rgb != nullptr);
+    const float *base0 = c0 < 3 ? p.d_out_rgb + c0 : p.d_out_lay + (c0 - 3), *base1 = c1 < 3 ? p.d_out_rgb + c1 : p.d_out_lay + (c1 - 3);
+    const unsigned stride0 = c0 < 3 ? 3u : (unsigned)K, stride1 = c1 < 3 ? 3u : (unsigned)K;
+    const long long row_words = (long long)W * CH;
     // a short queue (a handful of far pixels in an otherwise smooth flow) is spread over all warps instead of being
     // walked by a few of them: `per` entries per warp and round
     const unsigned per = min(32u, max(1u, (n_far + nw - 1u) / nw));
@@ -582,10 +590,11 @@ __global__ void __launch_bounds__(kThreads, VLG_FAR_CTAS) far_scatter_kernel(con
         const unsigned my_y = rem / (unsigned)W, my_x = rem - my_y * (unsigned)W;
         const unsigned my_q = (my_n * (unsigned)H + my_y) * (unsigned)p.pitch + my_x;     // pitched pixel index (< 2^32)
         const int my_x0 = (int)((unsigned)e.y & 0xFFFFu) - 8, my_y0 = (int)((unsigned)e.y >> 16) - 8;
+        const float my_fx = __int_as_float(e.z), my_fy = __int_as_float(e.w);
         unsigned my_modes = 0u;
+        const bool okw = my_x0 >= 0 && my_x0 < W, oke = my_x0 + 1 >= 0 && my_x0 + 1 < W;
+        const int txw = my_x0 >> 5, txe = (my_x0 + 1) >> 5;                           // kTW == 32
         {
-            const bool okw = my_x0 >= 0 && my_x0 < W, oke = my_x0 + 1 >= 0 && my_x0 + 1 < W;
-            const int txw = my_x0 >> 5, txe = (my_x0 + 1) >> 5;
             unsigned cnt[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -599,36 +608,66 @@ __global__ void __launch_bounds__(kThreads, VLG_FAR_CTAS) far_scatter_kernel(con
             for (int q = 0; q < 4; ++q)
                 if (far_seg_packed<K>(cnt[q])) my_modes |= (1u | ((unsigned)ceil_log2(cnt[q]) << 1)) << (5 * q);
         }
+        // The common case, prepared here once per entry instead of once per entry AND lane: both taps of a row lie in one
+        // packed segment (so a row is one run of 2 PW consecutive words), for every row inside the image.  Then the
+        // headroom 2^-h goes into the row weight (a power of two: the products round exactly as without it), and the run
+        // of row 0 starts at word  west * CH - xin * (CH - PW)  (west = pixel index of the west tap, xin = its column in the
+        // tile); row 1 lies W * CH words further.
+        const bool v0 = my_y0 >= 0 && my_y0 < H, v1 = my_y0 + 1 >= 0 && my_y0 + 1 < H;
+        const bool pairable = okw && oke && txw == txe;
+        const unsigned mr0 = my_modes & 31u, mr1 = (my_modes >> 10) & 31u;
+        const bool fast = (!v0 || (pairable && (mr0 & 1u))) && (!v1 || (pairable && (mr1 & 1u)));
+        const float my_wyh0 = __fmul_rn(__fsub_rn(1.0f, my_fy), pow2f(-(int)(mr0 >> 1))), my_wyh1 = __fmul_rn(my_fy, pow2f(-(int)(mr1 >> 1)));
+        const long long my_run = ((long long)(my_n * HWu) + (long long)my_y0 * W + my_x0) * CH - (long long)(my_x0 & 31) * (CH - PW);
+        // bits 0 / 1: row 0 / 1 receives something, bit 2: the fast path applies.  0 for the lanes past the end of the queue.
+        const unsigned my_flags = j < n_far ? ((v0 ? 1u : 0u) | (v1 ? 2u : 0u) | (fast ? 4u : 0u)) : 0u;
         const int nb = (int)min(per, n_far - base);
-        for (int k0 = 0; k0 < nb; k0 += U) {
-            unsigned fn[U], fmodes[U]; int fx0[U], fy0[U]; float ffx[U], ffy[U], d[U][ND], d0[U], d1[U];
+        for (int k0 = 0; k0 < nb; k0 += U) {                  // k0 + u <= 31: U divides 32
+            unsigned fl[U]; long long run[U]; float ffx[U], wyh0[U], wyh1[U], d0[U], d1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int sl = min(k0 + u, 31);
+                const int sl = k0 + u;
                 const unsigned i = __shfl_sync(0xffffffffu, my_i, sl), q = __shfl_sync(0xffffffffu, my_q, sl);
-                fn[u] = __shfl_sync(0xffffffffu, my_n, sl);
-                fx0[u] = __shfl_sync(0xffffffffu, my_x0, sl); fy0[u] = __shfl_sync(0xffffffffu, my_y0, sl);
-                ffx[u] = __int_as_float(__shfl_sync(0xffffffffu, e.z, sl)); ffy[u] = __int_as_float(__shfl_sync(0xffffffffu, e.w, sl));
-                fmodes[u] = __shfl_sync(0xffffffffu, my_modes, sl);
-                const float *drgb = p.d_out_rgb ? p.d_out_rgb + (int64_t)q * 3 : nullptr;
-                const float *dlay = p.d_out_lay ? p.d_out_lay + (int64_t)i * K : nullptr;
-#pragma unroll
-                for (int c0 = 0; c0 < CH; c0 += 32) {
-                    const int c = c0 + (int)lane;
-                    const float *src = c < 3 ? drgb : dlay;
-                    d[u][c0 / 32] = (c < CH && src != nullptr && k0 + u < nb) ? __ldg(src + (c < 3 ? c : c - 3)) : 0.f;
-                }
+                fl[u] = __shfl_sync(0xffffffffu, my_flags, sl);
+                run[u] = __shfl_sync(0xffffffffu, my_run, sl);
+                ffx[u] = __shfl_sync(0xffffffffu, my_fx, sl);
+                wyh0[u] = __shfl_sync(0xffffffffu, my_wyh0, sl); wyh1[u] = __shfl_sync(0xffffffffu, my_wyh1, sl);
+                // (lanes past the end of the queue point at pixel 0: a harmless load)
+                d0[u] = has0 ? __ldg(base0 + (size_t)(c0 < 3 ? q : i) * stride0) : 0.f;
+                d1[u] = has1 ? __ldg(base1 + (size_t)(c1 < 3 ? q : i) * stride1) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                d0[u] = d1[u] = 0.f;
-                if (FarPack<K>::can) {
-                    d0[u] = __shfl_sync(0xffffffffu, d[u][0], 2 * wd);
-                    d1[u] = __shfl_sync(0xffffffffu, d[u][0], (2 * wd + 1) & 31);
-                    if (2 * wd + 1 >= CH) d1[u] = 0.f;
+                if (fl[u] & 4u) {                                                     // warp-uniform
+                    if ((int)lane < 2 * PW) {
+                        const float wxs = side_of_lane ? ffx[u] : __fsub_rn(1.0f, ffx[u]);
+                        const float dd0 = __fmul_rn(d0[u], S0), dd1 = __fmul_rn(d1[u], S1);     // ... exact, |.| < 2^30
+                        long long *dst = p.far_acc + (run[u] + lane);
+                        if (fl[u] & 1u) {
+                            const float wt = __fmul_rn(wxs, wyh0[u]);
+                            const long long a0 = (long long)__float2int_rn(__fmul_rn(wt, dd0)), a1 = (long long)__float2int_rn(__fmul_rn(wt, dd1));
+                            atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)((a1 << 32) + a0));
+                        }
+                        if (fl[u] & 2u) {
+                            const float wt = __fmul_rn(wxs, wyh1[u]);
+                            const long long a0 = (long long)__float2int_rn(__fmul_rn(wt, dd0)), a1 = (long long)__float2int_rn(__fmul_rn(wt, dd1));
+                            atomicAdd(reinterpret_cast<unsigned long long *>(dst + row_words), (unsigned long long)((a1 << 32) + a0));
+                        }
+                    }
+                } else if (fl[u] & 3u) {                      // warp-uniform, rare: straddled tile borders, wide segments, other K
+                    const int sl = k0 + u;
+                    const unsigned i = __shfl_sync(0xffffffffu, my_i, sl), q = __shfl_sync(0xffffffffu, my_q, sl);
+                    float d[ND];
+#pragma unroll
+                    for (int cc0 = 0; cc0 < CH; cc0 += 32) {
+                        const int c = cc0 + (int)lane;
+                        const float *src = c < 3 ? (p.d_out_rgb ? p.d_out_rgb + (size_t)q * 3 + c : nullptr) : p.d_out_lay + (size_t)i * K + (c - 3);
+                        d[cc0 / 32] = (c < CH && src != nullptr) ? __ldg(src) : 0.f;
+                    }
+                    far_scatter_one<K>(p, lane, wd, side_of_lane, eg0, eg1, scale, __shfl_sync(0xffffffffu, my_n, sl),
+                                       __shfl_sync(0xffffffffu, my_x0, sl), __shfl_sync(0xffffffffu, my_y0, sl), ffx[u],
+                                       __shfl_sync(0xffffffffu, my_fy, sl), __shfl_sync(0xffffffffu, my_modes, sl), d, d0[u], d1[u]);
                 }
-                if (k0 + u < nb)                                                      // warp-uniform
-                    far_scatter_one<K>(p, lane, wd, side_of_lane, eg0, eg1, scale, fn[u], fx0[u], fy0[u], ffx[u], ffy[u], fmodes[u], d[u], d0[u], d1[u]);
             }
         }
     }
