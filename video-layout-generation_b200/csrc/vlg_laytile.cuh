@@ -99,6 +99,7 @@ struct LayTileSmem {
     unsigned cnt[2];                            // warps that have finished the tile using window buffer b
     float red[kTH][4];
     int last;
+    int seen[kFarSeen];                         // tiles this CTA has already flagged as far targets (far_announce)
 };
 
 // PX8: the tensor map describes rows of 8-byte units (pixels whose byte size is not a multiple of 16, e.g.
@@ -215,6 +216,8 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
 #endif
     if (tid < 2) { mbar_init(&sm.bar[tid], 1); sm.cnt[tid] = 0u; }
     if (tid < 8) sm.acc[tid >> 2][tid & 3] = 0;
+    static_assert(kFarSeen == kThreads, "one entry per thread");
+    sm.seen[tid] = -1;
     float2 f0 = load_coords(0, g0), f1 = load_coords(1, g1);
     float2 xy0, xy1;
     {
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, VLG_LAYTILE_MIN_BLOCKS) lay_tile_ker
             if (p.far_list) {
                 p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = make_int4((int)(img + (int64_t)y * W + x), (tp.x0 + 8) | ((tp.y0 + 8) << 16),
                                                                           __float_as_int(tp.ix - tp.fx0), __float_as_int(tp.iy - tp.fy0));
-                far_announce(p.tile_flags, p.flagged_list, p.seg_cnt, p.hdr, g.n, tiles_x, tiles_y, tp.x0, tp.y0, W, H);
+                far_announce(p.tile_flags, p.flagged_list, p.seg_cnt, p.hdr, g.n, tiles_x, tiles_y, tp.x0, tp.y0, W, H, sm.seen);
             } else {
                 atomicOr(&p.hdr->status, VLG_STATUS_FAR_TAPS);
             }

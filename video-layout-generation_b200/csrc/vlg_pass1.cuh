@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, VLG_P1_MIN_BLOCKS) pass1_kernel(cons
                 if (p.far_list) {
                     p.far_list[atomicAdd(&p.hdr->far_count, 1u)] = make_int4((int)(img_px + o), (t.x0 + 8) | ((t.y0 + 8) << 16),
                                                                               __float_as_int(t.ix - t.fx0), __float_as_int(t.iy - t.fy0));
-                    far_announce(p.tile_flags, p.flagged_list, p.seg_cnt, p.hdr, n, p.tiles_x, p.tiles_y, t.x0, t.y0, W, H);
+                    far_announce(p.tile_flags, p.flagged_list, p.seg_cnt, p.hdr, n, p.tiles_x, p.tiles_y, t.x0, t.y0, W, H, nullptr);
                 } else {
                     atomicOr(&p.hdr->status, VLG_STATUS_FAR_TAPS);
                 }
