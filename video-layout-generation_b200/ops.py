@@ -113,8 +113,36 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+# torch.cuda.current_stream() and the torch.cuda.device() context manager cost 15-20 us of Python each (device-index
+# resolution, availability checks); an end-to-end step used a dozen of them -- a fifth of its host time.  The raw
+# accessors below are what they end in.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    """The current stream of the current device as a ctypes pointer."""
+    if _raw_stream is not None and _raw_device is not None:
+        return C.c_void_p(_raw_stream(_raw_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(dev):
+    """Context that makes `dev` current -- a no-op object when it already is (the usual case: one process per GPU)."""
+    if _raw_device is not None and dev is not None and dev.index is not None and _raw_device() == dev.index:
+        return _NO_SWITCH
+    return torch.cuda.device(dev)
 
 
 def _class_weight_ptr(cfg: "WarpLossConfig", K: int):
@@ -160,7 +188,11 @@ def _workspace(prob: Problem, with_src: bool, device, cached: bool = True) -> to
         raise VlgError(lib.vlg_last_error().decode())
     if not cached:
         return torch.empty(n, dtype=torch.uint8, device=device)
-    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    device = torch.device(device)
+    if _raw_stream is not None and device.index is not None:
+        key = (device.index, _raw_stream(device.index))
+    else:
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < n:
         if len(_WS_CACHE) >= 8:
@@ -207,7 +239,7 @@ def warp(src_rgb: Optional[torch.Tensor], src_layout: Optional[torch.Tensor], co
     out_lay = empty_nhwc((N, K, H, W), ref.dtype, dev) if (b is not None and want_layout) else None
     out_arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if (b is not None and want_argmax) else None
     dbg = torch.empty((N, H, W, 2), dtype=torch.int32, device=dev) if debug_indices else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib.vlg_warp_fwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(coords), _ptr(out_rgb), _ptr(out_lay),
                                _ptr(out_arg), _ptr(dbg), _stream()))
     res = (out_rgb, out_lay, out_arg)
@@ -233,7 +265,7 @@ def warp_labels(src_rgb: Optional[torch.Tensor], src_label: torch.Tensor, coords
     lab = src_label.contiguous()
     out_rgb = empty_nhwc((N, 3, H, W), dt, lab.device) if a is not None else None
     out_lab = torch.empty_like(lab)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib.vlg_warp_fwd_labels(C.byref(prob), _ptr(a), _ptr(lab), _ptr(coords), _ptr(out_rgb), _ptr(out_lab), _stream()))
     return out_rgb, out_lab
 
@@ -268,7 +300,7 @@ def colorize(seg: torch.Tensor, n_classes: int = 20, argmax: bool = False, palet
         lay, lab, dt = None, seg.contiguous(), dtype
     prob = _problem(N, H, W, n_classes, dt, WarpLossConfig())
     out = empty_nhwc((N, 3, H, W), dt, seg.device)
-    with torch.cuda.device(seg.device):
+    with _on(seg.device):
         check(lib.vlg_colorize(C.byref(prob), _ptr(lay), _ptr(lab), _ptr(lut), _ptr(out), None, _stream()))
     return out
 
@@ -293,7 +325,7 @@ def one_hot_layout(seg: torch.Tensor, n_classes: int = 20, dtype: torch.dtype = 
     out = empty_nhwc((N, n_classes, H, W), dtype, seg.device)
     lib = _cabi.load()
     li, lf = (_ptr(seg), None) if seg.dtype == torch.int64 else (None, _ptr(seg))
-    with torch.cuda.device(seg.device):
+    with _on(seg.device):
         check(lib.vlg_one_hot(C.byref(prob), li, lf, _ptr(out), None, _stream()))
     return out
 
@@ -330,10 +362,24 @@ def prepare_frames(frames: torch.Tensor, mean=IMG_MEAN, std=IMG_STD, *, flip: bo
             raise VlgError(f"labels must be int64 [N,H,W]={N, H, W}")
         labels = labels.contiguous()
         lab_out = torch.empty_like(labels)
-    with torch.cuda.device(frames.device):
+    with _on(frames.device):
         check(_cabi.load().vlg_frame_affine(C.byref(prob), _ptr(frames), int(not nhwc), a3, b3, int(denormalize), int(flip),
                                             _ptr(out), _ptr(labels), _ptr(lab_out), _stream()))
     return out if labels is None else (out, lab_out)
+
+
+_F3_CACHE: dict = {}
+
+
+def _float3(v):
+    """(C float)[3] of a mean / std triple, cached by value."""
+    if v is None:
+        return None
+    key = tuple(float(x) for x in v)
+    arr = _F3_CACHE.get(key)
+    if arr is None:
+        arr = _F3_CACHE[key] = (C.c_float * 3)(*key)
+    return arr
 
 
 @torch.no_grad()
@@ -372,9 +418,8 @@ def ingest(frames_u8: Optional[torch.Tensor] = None, seg_u8: Optional[torch.Tens
             out["one_hot"] = empty_nhwc((N, n_classes, H, W), dtype, dev)
         if not (want_label or want_seg_float or want_one_hot):
             raise VlgError("seg_u8 given but no output requested for it")
-    m3 = (C.c_float * 3)(*[float(v) for v in mean]) if mean is not None else None
-    s3 = (C.c_float * 3)(*[float(v) for v in std]) if mean is not None else None
-    with torch.cuda.device(dev):
+    m3, s3 = _float3(mean), (_float3(std) if mean is not None else None)
+    with _on(dev):
         check(_cabi.load().vlg_ingest(C.byref(prob), _ptr(f_in), m3, s3, int(flip), _ptr(out.get("frames")), _ptr(s_in),
                                       _ptr(out.get("label")), _ptr(out.get("seg_float")), _ptr(out.get("one_hot")), None, _stream()))
     return out
@@ -424,7 +469,7 @@ class _WarpLossFn(torch.autograd.Function):
         d_a = empty_nhwc(a.shape, dt, dev) if need_src else None
         d_b = empty_nhwc(b.shape, dt, dev) if need_src else None
         arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if cfg.want_argmax else None
-        with torch.cuda.device(dev):
+        with _on(dev):
             check(lib.vlg_warp_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(b), _ptr(c), _ptr(t), _ptr(lab), _ptr(loss),
                                             _ptr(d_c), _ptr(d_a), _ptr(d_b), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
             if cfg.debug:
@@ -443,7 +488,7 @@ class _WarpLossFn(torch.autograd.Function):
         lib = _cabi.load()
         d_a, d_b, d_c = ctx.grads
         g = g_total.detach().to(torch.float32).contiguous()
-        with torch.cuda.device(g.device):
+        with _on(g.device):
             for t in (d_a, d_b, d_c):
                 if t is not None:
                     check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
@@ -475,7 +520,7 @@ class _WarpLossLabelsFn(torch.autograd.Function):
         loss = torch.empty(_cabi.LOSS_SLOTS, dtype=torch.float32, device=dev)
         d_c = torch.empty_like(c) if need_c else None
         arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if cfg.want_argmax else None
-        with torch.cuda.device(dev):
+        with _on(dev):
             check(lib.vlg_warp_loss_labels_fwd_bwd(C.byref(prob), _ptr(a), _ptr(src_label.contiguous()), _ptr(c), _ptr(t),
                                                    _ptr(tgt_label.contiguous()), _ptr(loss), _ptr(d_c), _ptr(arg), _ptr(ws),
                                                    ws.numel(), _stream()))
@@ -495,7 +540,7 @@ class _WarpLossLabelsFn(torch.autograd.Function):
         d_c = ctx.grad_c
         if d_c is not None:
             g = g_total.detach().to(torch.float32).contiguous()
-            with torch.cuda.device(g.device):
+            with _on(g.device):
                 check(_cabi.load().vlg_scale_grads(_ptr(d_c), d_c.numel(), _cabi.F32, _ptr(g), _stream()))
         return None, None, d_c, None, None, None, None
 
@@ -551,7 +596,7 @@ class _PixelLossFn(torch.autograd.Function):
         d_a = empty_nhwc(a.shape, dt, dev) if need_a else None
         d_z = empty_nhwc(z.shape, dt, dev) if need_z else None
         arg = torch.empty((N, H, W), dtype=torch.int64, device=dev) if (cfg.want_argmax and z is not None) else None
-        with torch.cuda.device(dev):
+        with _on(dev):
             check(lib.vlg_pixel_loss_fwd_bwd(C.byref(prob), _ptr(a), _ptr(t), _ptr(z), _ptr(lab), _ptr(loss), _ptr(d_a),
                                              _ptr(d_z), _ptr(arg), _ptr(ws), ws.numel(), _stream()))
             if cfg.debug:
@@ -569,7 +614,7 @@ class _PixelLossFn(torch.autograd.Function):
         lib = _cabi.load()
         d_a, d_z = ctx.grads
         g = g_total.detach().to(torch.float32).contiguous()
-        with torch.cuda.device(g.device):
+        with _on(g.device):
             for t in (d_a, d_z):
                 if t is not None:
                     check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
@@ -584,6 +629,6 @@ def pixel_losses(out_rgb, tgt_rgb, logits, tgt_label, cfg: Optional[WarpLossConf
 def read_status(workspace: torch.Tensor) -> int:
     """Synchronising debug helper: VLG_STATUS_* bits left by the last pass on this workspace."""
     st = C.c_uint32(0)
-    with torch.cuda.device(workspace.device):
+    with _on(workspace.device):
         check(_cabi.load().vlg_read_status(_ptr(workspace), workspace.numel(), C.byref(st), _stream()))
     return st.value
