@@ -65,6 +65,30 @@ def test_problem_struct_layout_matches_c():
     assert P().struct_size == vals[0] and P().abi_version == _cabi.ABI_VERSION
 
 
+def test_python_constants_match_the_header():
+    """Every VLG_FLAG_* / VLG_TERM_* / VLG_STATUS_* / VLG_CE_NORM_* / VLG_NEAR_RADIUS the Python side mirrors has the
+    value the header (as gcc sees it) gives it -- a flag added on one side only would silently select another path."""
+    names = {"VLG_FLAG_NO_FAR_PATH": _cabi.FLAG_NO_FAR_PATH, "VLG_FLAG_NO_TMA": _cabi.FLAG_NO_TMA,
+             "VLG_FLAG_TILE_RGB": _cabi.FLAG_TILE_RGB, "VLG_FLAG_TILE_LAYOUT": _cabi.FLAG_TILE_LAYOUT,
+             "VLG_FLAG_PASS2_COORDS": _cabi.FLAG_PASS2_COORDS, "VLG_FLAG_FAR_WIDE": _cabi.FLAG_FAR_WIDE,
+             "VLG_TERM_L1": _cabi.TERM_L1, "VLG_TERM_GD": _cabi.TERM_GD, "VLG_TERM_SSIM": _cabi.TERM_SSIM,
+             "VLG_TERM_CE": _cabi.TERM_CE, "VLG_TERM_TV": _cabi.TERM_TV,
+             "VLG_STATUS_BAD_LABEL": _cabi.STATUS_BAD_LABEL, "VLG_STATUS_FAR_TAPS": _cabi.STATUS_FAR_TAPS,
+             "VLG_CE_NORM_TORCH": _cabi.CE_NORM_TORCH, "VLG_CE_NORM_COUNT": _cabi.CE_NORM_COUNT,
+             "VLG_NEAR_RADIUS": _cabi.NEAR_RADIUS}
+    src = '#include <stdio.h>\n#include "vlg_b200.h"\nint main(void){\n' + "".join(
+        f'printf("%lld ", (long long)({n}));\n' for n in names) + "return 0; }\n"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
+        vals = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert dict(zip(names, vals)) == names
+    flags = [v for n, v in names.items() if n.startswith("VLG_FLAG_")]
+    assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags), "flags are distinct single bits"
+
+
 def test_integration_doc_binding_matches_c():
     """INTEGRATION.md shows a maintainer the ctypes mirror of vlg_problem_t: the DOCUMENT is what gets copied, so
     the snippet itself is executed here and its layout compared with the header (round 1 shipped a stale one)."""
