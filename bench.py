@@ -434,14 +434,19 @@ def u8_host_inputs(d, K):
     return {k: v.cpu().pin_memory() for k, v in host.items()}
 
 
-def e2e_fused(cx: Ctx, fz: Fused, steps, flow_from_host=False):
+def e2e_fused(cx: Ctx, fz: Fused, steps, flow_from_host=False, captured=True):
     """End to end through the public API (vlg_b200.ingest + vlg_b200.WarpLoss + backward) from pinned host memory.
     Every step uploads one full input set -- what the dataset holds: uint8 frames and class maps -- and reads the
     step's loss vector back.  Double-buffered: the inputs of step i+1 travel on a copy stream while step i computes
     (what a DataLoader prefetcher does).  The flow is NOT part of the dataset: in the reference's step it is the
     network's output (src/trainer.py:183-210: frames and class maps are uploaded, the network computes its output from them) and never exists on the host, so it
     is device-resident here (two alternating flow fields); `flow_from_host=True` uploads it as well (the round-1/2
-    figure, kept as `flow_uploaded` for comparison)."""
+    figure, kept as `flow_uploaded` for comparison).
+
+    `captured=True`: the step's device work -- the SAME public calls: ingest x2, WarpLoss, backward() -- is recorded once
+    per input buffer set with `vlg_b200.CapturedStep` (torch.cuda.graph whole-step capture, the package's utility for
+    static shapes) and replayed; uploads, the replay and the loss read-back still happen every step.  `captured=False`
+    issues the calls eagerly every step (bound by ~0.45 ms of host time per step)."""
     vlg, dev, stream = cx.vlg, cx.dev, cx.stream
     host = u8_host_inputs(fz.sets[0], fz.K)
     if not flow_from_host:
@@ -467,10 +472,8 @@ def e2e_fused(cx: Ctx, fz: Fused, steps, flow_from_host=False):
     res_done = [torch.cuda.Event(), torch.cuda.Event()]
     seen = []
 
-    def e2e_step(i):
-        j = i & 1
-        upload(j ^ 1)                      # inputs of the NEXT step
-        stream.wait_event(up_done[j])
+    def device_step(j):
+        """The step's device work on buffer set j, through the public API; returns the loss vector."""
         cur = dbuf[j]
         src = vlg.ingest(cur["src_u8"], cur["src_seg_u8"], n_classes=fz.K, dtype=fz.tdt, want_label=False, want_one_hot=True)
         tgt = vlg.ingest(cur["tgt_u8"], cur["tgt_seg_u8"], n_classes=fz.K, dtype=fz.tdt, want_label=True)
@@ -479,8 +482,30 @@ def e2e_fused(cx: Ctx, fz: Fused, steps, flow_from_host=False):
         f = (cur["flow"] if flow_from_host else dev_flow[j]).detach().requires_grad_(True)
         total = crit(a, b, f, tgt["frames"], tgt["label"])
         total.backward()
+        return crit.last_terms
+
+    mode = "eager"
+    run_step = device_step
+    if captured:
+        try:
+            for j in range(2):                  # the buffers hold valid data before anything is recorded
+                for k, v in host.items():
+                    dbuf[j][k].copy_(v)
+            torch.cuda.synchronize()
+            graphs = [vlg.CapturedStep(lambda j=j: device_step(j)) for j in range(2)]
+            run_step = lambda j: graphs[j]()
+            mode = "captured"
+        except Exception as exc:               # capture unsupported here: the eager call sequence
+            print(f"[bench] whole-step capture failed ({exc}); e2e runs eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+
+    def e2e_step(i):
+        j = i & 1
+        upload(j ^ 1)                      # inputs of the NEXT step
+        stream.wait_event(up_done[j])
+        terms = run_step(j)
         consumed[j].record(stream)
-        res_host[j].copy_(crit.last_terms, non_blocking=True)     # device -> host read of the step's result
+        res_host[j].copy_(terms, non_blocking=True)               # device -> host read of the step's result
         res_done[j].record(stream)
         if i > 0:                          # the previous step's result has landed by now (or is waited for here)
             res_done[j ^ 1].synchronize()
@@ -510,6 +535,9 @@ def e2e_fused(cx: Ctx, fz: Fused, steps, flow_from_host=False):
     ms = cx.max_over_ranks(e0.elapsed_time(e1) / n)
     return {"value": cx.world * fz.P / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": cx.cabi.LOSS_SLOTS * 4, "ms_per_step": ms, "steps": n,
+            "launch": {"captured": "the step's public calls (vlg_b200.ingest x2, WarpLoss, backward) recorded once per buffer set with "
+                                   "vlg_b200.CapturedStep and replayed every step",
+                       "eager": "the step's public calls issued from Python every step"}[mode],
             "inputs": "pinned host, what the dataset holds (src/folder.py:85-104): uint8 RGB frames [N,H,W,3] x2, uint8 class maps "
                       "[N,H,W] x2" + (", and the fp32 flow = 16 B/px" if flow_from_host else " = 8 B/px; the flow is the network's output in "
                       "the reference's step (src/trainer.py:183-210) and stays on the device") + "; on the device vlg_ingest turns them into normalised NHWC frames, int64 "
@@ -741,6 +769,8 @@ def main():
 
     # ---- timed region 2: end to end through the public module API from pinned host memory ----
     e2e = e2e_fused(cx, fz, args.steps)
+    eg = e2e_fused(cx, fz, args.steps, captured=False)
+    e2e["eager"] = {k: eg[k] for k in ("value", "unit", "ms_per_step", "launch")}
     up = e2e_fused(cx, fz, args.steps, flow_from_host=True)
     e2e["flow_uploaded"] = {k: up[k] for k in ("value", "unit", "h2d_bytes_per_step", "ms_per_step")}
 

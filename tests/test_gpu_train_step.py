@@ -204,3 +204,49 @@ def test_optimiser_step_matches_the_oracle_driven_step():
         opt.step()
         first = loss.item() if first is None else first
     assert loss.item() < first
+
+
+def test_captured_step_replays_the_eager_step_bitwise():
+    """vlg_b200.CapturedStep: the step's public calls (ingest, WarpLoss, backward) recorded once with torch.cuda.graph
+    and replayed on NEW data copied into the static buffers give, bit for bit, the loss vector and the gradients of the
+    eager call sequence on that data (the kernels are deterministic); and backward() hands its gradient buffers over to
+    autograd without a copy (the .grad of a leaf IS the buffer the fused pass wrote)."""
+    N, H, W, K = 2, 40, 72, 20
+    g = torch.Generator().manual_seed(31)
+    mk = lambda: dict(src=torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(DEV),
+                      tgt=torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(DEV),
+                      sseg=torch.randint(0, K, (N, H, W), generator=g).to(torch.uint8).to(DEV),
+                      tseg=torch.randint(0, K, (N, H, W), generator=g).to(torch.uint8).to(DEV),
+                      flow=(torch.randn(N, H, W, 2, generator=g) * 1.5).to(DEV))
+    crit = vlg_b200.WarpLoss(weights=(40.0, 20.0, 10.0, 0.5))
+
+    def step(buf):
+        src = vlg_b200.ingest(buf["src"], buf["sseg"], n_classes=K, want_label=False, want_one_hot=True)
+        tgt = vlg_b200.ingest(buf["tgt"], buf["tseg"], n_classes=K, want_label=True)
+        a, b = src["frames"].requires_grad_(True), src["one_hot"].requires_grad_(True)
+        f = buf["flow"].detach().requires_grad_(True)
+        crit(a, b, f, tgt["frames"], tgt["label"]).backward()
+        return crit.last_terms, a.grad, b.grad, f.grad
+
+    static = mk()
+    cap = vlg_b200.CapturedStep(lambda: step(static))
+    for _ in range(2):
+        new = mk()
+        want = [t.clone() for t in step(new)]
+        for k in static:
+            static[k].copy_(new[k])
+        got = cap()
+        torch.cuda.synchronize()
+        for w, x in zip(want, got):
+            assert torch.equal(w, x)
+
+    # eager backward: no clone of the gradient buffers
+    buf = mk()
+    src = vlg_b200.ingest(buf["src"], buf["sseg"], n_classes=K, want_label=False, want_one_hot=True)
+    tgt = vlg_b200.ingest(buf["tgt"], buf["tseg"], n_classes=K, want_label=True)
+    a, b = src["frames"].requires_grad_(True), src["one_hot"].requires_grad_(True)
+    f = buf["flow"].detach().requires_grad_(True)
+    total, terms, _ = vlg_b200.warp_loss(a, b, f, tgt["frames"], tgt["label"], crit.cfg)
+    ptrs = [t.data_ptr() for t in total.grad_fn.grads]
+    total.backward()
+    assert [a.grad.data_ptr(), b.grad.data_ptr(), f.grad.data_ptr()] == ptrs

@@ -6,6 +6,7 @@ root; the directory name carries a hyphen).
 """
 from . import _build, _cabi  # noqa: F401
 from ._cabi import VlgError, launch_count  # noqa: F401
+from .graphs import CapturedStep  # noqa: F401
 from .losses import (CombinedLoss, CrossEntropyLoss, GradientLoss, L1Loss, PixelLosses,  # noqa: F401
                      SsimLoss, WarpLoss)
 from .ops import (CITYSCAPES_PALETTE, WarpLossConfig, colorize, empty_nhwc, ingest, one_hot_layout, pixel_losses, prepare_frames,  # noqa: F401

@@ -487,6 +487,7 @@ class _WarpLossFn(torch.autograd.Function):
         ctx.consumed = True
         lib = _cabi.load()
         d_a, d_b, d_c = ctx.grads
+        ctx.grads = None     # sole owner from here on: autograd adopts the buffers as .grad instead of cloning them (a 100 B/px copy)
         g = g_total.detach().to(torch.float32).contiguous()
         with _on(g.device):
             for t in (d_a, d_b, d_c):
@@ -537,7 +538,7 @@ class _WarpLossLabelsFn(torch.autograd.Function):
         if ctx.consumed:
             raise VlgError("the fused warp-loss gradients were already consumed (retain_graph is unsupported)")
         ctx.consumed = True
-        d_c = ctx.grad_c
+        d_c, ctx.grad_c = ctx.grad_c, None     # see _WarpLossFn.backward
         if d_c is not None:
             g = g_total.detach().to(torch.float32).contiguous()
             with _on(g.device):
@@ -613,6 +614,7 @@ class _PixelLossFn(torch.autograd.Function):
         ctx.consumed = True
         lib = _cabi.load()
         d_a, d_z = ctx.grads
+        ctx.grads = None     # see _WarpLossFn.backward
         g = g_total.detach().to(torch.float32).contiguous()
         with _on(g.device):
             for t in (d_a, d_z):
