@@ -340,11 +340,13 @@ class Fused:
                         self.launch_fused(s, self._sp())
                     gs.append(g)
                 else:   # two graphs per input set: the all-reduce is issued between them
-                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    g1, g2 = torch.cuda.CUDAGraph(), None
                     with torch.cuda.graph(g1):
                         self.launch_pass1(s, self._sp())
-                    with torch.cuda.graph(g2):
-                        self.launch_pass2(s, self._sp())
+                    if self.with_src:          # sources as data: there is no pass 2 (an empty capture only earns a warning)
+                        g2 = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g2):
+                            self.launch_pass2(s, self._sp())
                     gs.append((g1, g2))
             self.launches_per_step = (cx.vlg.launch_count() - n_before) // len(self.sets)
             self.graphs = gs
@@ -367,7 +369,8 @@ class Fused:
             if self.graphs is not None: self.graphs[k][0].replay()
             else: self.launch_pass1(s, sp)
             work = cx.dist.all_reduce(self.loss, async_op=True)
-            if self.graphs is not None: self.graphs[k][1].replay()
+            if self.graphs is not None:
+                if self.graphs[k][1] is not None: self.graphs[k][1].replay()
             else: self.launch_pass2(s, sp)
             work.wait()
         elif self.graphs is not None:
