@@ -247,6 +247,12 @@ int vlg_pixel_loss_fwd_bwd(const vlg_problem_t *prob, const void *out_rgb, const
  * `loss.backward()` case), so autograd semantics cost one empty launch.  `scale` is a device ptr. */
 int vlg_scale_grads(void *g, int64_t n, int32_t dtype, const float *scale, void *stream);
 
+/* The same for `count` (<= 4) buffers in one launch: g[b] has n[b] elements of dtype[b] (HOST arrays of device
+ * pointers / sizes / dtypes, read at call time).  What `loss.backward()` (src/trainer.py:257) costs the fused op: one
+ * launch that finds *scale == 1.0f and exits, instead of one per gradient tensor. */
+int vlg_scale_grads_multi(int32_t count, void *const *g, const int64_t *n, const int32_t *dtype, const float *scale,
+                          void *stream);
+
 /* Copies the device status word (VLG_STATUS_*) to *host_status.  Synchronises `stream`. */
 int vlg_read_status(void *workspace, size_t workspace_bytes, uint32_t *host_status, void *stream);
 

@@ -353,10 +353,11 @@ def test_upstream_gradient_scaling():
     grads = []
     for scale in (1.0, 0.125):
         a = _cl(d["src_rgb"]).requires_grad_(True)
+        b = _cl(d["src_layout"]).requires_grad_(True)
         f = d["flow"].to(DEV).requires_grad_(True)
-        total, _, _ = vlg_b200.warp_loss(a, _cl(d["src_layout"]), f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV))
+        total, _, _ = vlg_b200.warp_loss(a, b, f, _cl(d["tgt_rgb"]), d["tgt_label"].to(DEV))
         (total * scale).backward()
-        grads.append((a.grad.clone(), f.grad.clone()))
+        grads.append((a.grad.clone(), b.grad.clone(), f.grad.clone()))     # one vlg_scale_grads_multi launch for the three
     for g1, g2 in zip(*grads):
         assert torch.equal(g1 * 0.125, g2)   # power-of-two scale is exact
 

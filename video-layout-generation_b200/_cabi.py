@@ -28,7 +28,7 @@ EXPORTS = [
     "vlg_frame_affine", "vlg_ingest", "vlg_warp_loss_labels_fwd_bwd",
     "vlg_warp_loss_bwd_out", "vlg_warp_loss_pass1",
     "vlg_warp_bwd_src", "vlg_reduce_partials", "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd",
-    "vlg_scale_grads", "vlg_read_status", "vlg_launch_count", "vlg_timeline_arm", "vlg_timeline_read",
+    "vlg_scale_grads", "vlg_scale_grads_multi", "vlg_read_status", "vlg_launch_count", "vlg_timeline_arm", "vlg_timeline_read",
 ]
 
 
@@ -116,13 +116,14 @@ def load(build_if_missing: bool = True):
     lib.vlg_warp_loss_fwd_bwd.argtypes = [P, vp, vp, f32p, vp, i64p, f32p, f32p, vp, vp, i64p, vp, C.c_size_t, vp]
     lib.vlg_pixel_loss_fwd_bwd.argtypes = [P, vp, vp, vp, i64p, f32p, vp, vp, i64p, vp, C.c_size_t, vp]
     lib.vlg_scale_grads.argtypes = [vp, C.c_int64, C.c_int32, f32p, vp]
+    lib.vlg_scale_grads_multi.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32), f32p, vp]
     lib.vlg_read_status.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint32), vp]
     lib.vlg_timeline_arm.argtypes = [C.c_int]
     lib.vlg_timeline_arm.restype = C.c_int
     lib.vlg_timeline_read.argtypes = [C.POINTER(C.c_float)]
     lib.vlg_timeline_read.restype = C.c_int
     for name in ("vlg_warp_fwd", "vlg_warp_fwd_labels", "vlg_warp_loss_bwd_out", "vlg_warp_bwd_src", "vlg_reduce_partials",
-                 "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd", "vlg_scale_grads", "vlg_read_status"):
+                 "vlg_warp_loss_fwd_bwd", "vlg_pixel_loss_fwd_bwd", "vlg_scale_grads", "vlg_scale_grads_multi", "vlg_read_status"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -262,6 +262,24 @@ __global__ void scale_kernel(T *g, int64_t n, const float *scale) {
         g[i] = from_f<T>(to_f<T>(g[i]) * s);
 }
 
+// The same for up to four buffers in ONE launch (autograd's backward of the fused op rescales d_src_rgb, d_src_layout and
+// d_coords: three launches that almost always find *scale == 1 and exit).
+struct ScaleSet { void *g[4]; int64_t n[4]; int dtype[4]; int count; };
+__global__ void scale_multi_kernel(ScaleSet s, const float *scale) {
+    const float f = __ldg(scale);
+    if (f == 1.0f) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int b = 0; b < s.count; ++b) {
+        if (s.dtype[b] == VLG_F32) {
+            float *g = (float *)s.g[b];
+            for (int64_t i = t0; i < s.n[b]; i += stride) g[i] = g[i] * f;
+        } else {
+            __nv_bfloat16 *g = (__nv_bfloat16 *)s.g[b];
+            for (int64_t i = t0; i < s.n[b]; i += stride) g[i] = from_f<__nv_bfloat16>(to_f<__nv_bfloat16>(g[i]) * f);
+        }
+    }
+}
+
 // Rollout warp with LABEL sources: the layout fed back between rollout steps is
 // argmax -> one-hot (src/trainer.py:467), so the 20-channel gather collapses to four int64 taps.
 // out_label == argmax_c warp(one_hot(src_label))_c bit for bit: for a 0/1 source the dense FMA
@@ -1271,6 +1289,19 @@ int vlg_scale_grads(void *g, int64_t n, int32_t dtype, const float *scale, void 
     else if (dtype == VLG_BF16) scale_kernel<__nv_bfloat16><<<sm_count() * 8, 256, 0, st>>>((__nv_bfloat16 *)g, n, scale);
     else return fail(VLG_ERR_ARG, "bad dtype");
     return check_launch("scale_kernel");
+}
+
+int vlg_scale_grads_multi(int32_t count, void *const *g, const int64_t *n, const int32_t *dtype, const float *scale, void *stream) {
+    if (count < 0 || count > 4 || !scale || (count && (!g || !n || !dtype))) return fail(VLG_ERR_ARG, "bad arguments to vlg_scale_grads_multi");
+    ScaleSet s{};
+    for (int b = 0; b < count; ++b) {
+        if (!g[b] || n[b] < 0 || (dtype[b] != VLG_F32 && dtype[b] != VLG_BF16)) return fail(VLG_ERR_ARG, "vlg_scale_grads_multi: bad buffer %d", b);
+        if (n[b] == 0) continue;
+        s.g[s.count] = g[b]; s.n[s.count] = n[b]; s.dtype[s.count] = dtype[b]; ++s.count;
+    }
+    if (s.count == 0) return VLG_OK;
+    scale_multi_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(s, scale);
+    return check_launch("scale_multi_kernel");
 }
 
 int vlg_read_status(void *workspace, size_t workspace_bytes, uint32_t *host_status, void *stream) {

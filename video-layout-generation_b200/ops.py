@@ -438,6 +438,20 @@ def rollout(img: torch.Tensor, label: torch.Tensor, flow_fn, steps: int = 5, *, 
     return imgs[1:], labels[1:]
 
 
+def _scale_all(tensors, g_total):
+    """g <- g * g_total for every gradient buffer, on the device, in ONE launch (it exits at once when g_total == 1)."""
+    ts = [t for t in tensors if t is not None]
+    if not ts:
+        return
+    g = g_total.detach().to(torch.float32).contiguous()
+    n = len(ts)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    sizes = (C.c_int64 * n)(*[t.numel() for t in ts])
+    dts = (C.c_int32 * n)(*[_DTYPES[t.dtype] for t in ts])
+    with _on(g.device):
+        check(_cabi.load().vlg_scale_grads_multi(n, ptrs, sizes, dts, _ptr(g), _stream()))
+
+
 # --------------------------------------------------------------------------- fused warp + loss
 class _WarpLossFn(torch.autograd.Function):
     """Fused forward+backward: the gradients are produced by the SAME pass as the losses (for an
@@ -488,11 +502,7 @@ class _WarpLossFn(torch.autograd.Function):
         lib = _cabi.load()
         d_a, d_b, d_c = ctx.grads
         ctx.grads = None     # sole owner from here on: autograd adopts the buffers as .grad instead of cloning them (a 100 B/px copy)
-        g = g_total.detach().to(torch.float32).contiguous()
-        with _on(g.device):
-            for t in (d_a, d_b, d_c):
-                if t is not None:
-                    check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
+        _scale_all((d_a, d_b, d_c), g_total)
         return d_a, d_b, d_c, None, None, None
 
 
@@ -615,11 +625,7 @@ class _PixelLossFn(torch.autograd.Function):
         lib = _cabi.load()
         d_a, d_z = ctx.grads
         ctx.grads = None     # see _WarpLossFn.backward
-        g = g_total.detach().to(torch.float32).contiguous()
-        with _on(g.device):
-            for t in (d_a, d_z):
-                if t is not None:
-                    check(lib.vlg_scale_grads(_ptr(t), t.numel(), _DTYPES[t.dtype], _ptr(g), _stream()))
+        _scale_all((d_a, d_z), g_total)
         return d_a, None, d_z, None, None
 
 
