@@ -957,6 +957,23 @@ static int launch_frame_affine(const vlg_problem_t *prob, const FrameAffine &fa,
 }
 
 // ------------------------------------------------------------------ exported C ABI
+template <typename T, int K>
+static int launch_ingest_seg(int64_t P, int W, int flip, const uint8_t *seg_u8, int64_t *out_label, float *out_seg_f32, void *out_onehot,
+                             void *workspace, cudaStream_t st) {
+    constexpr int EPC = 16 / (int)sizeof(T);
+    if constexpr (K % EPC == 0) {
+        if (out_onehot) {     // one thread per 16-byte chunk of the one-hot layout
+            const int64_t n = ((P + 31) / 32) * 32;      // one warp per 32 pixels
+            ingest_seg_kernel<T, K, true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, W, flip, seg_u8, out_label, out_seg_f32, (T *)out_onehot,
+                                                                                       (WsHeader *)workspace);
+            return check_launch("ingest_seg_kernel");
+        }
+    }
+    ingest_seg_kernel<T, K, false><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, W, flip, seg_u8, out_label, out_seg_f32, (T *)out_onehot,
+                                                                                (WsHeader *)workspace);
+    return check_launch("ingest_seg_kernel");
+}
+
 extern "C" {
 
 int vlg_version(void) { return VLG_VERSION; }
@@ -1216,16 +1233,8 @@ int vlg_ingest(const vlg_problem_t *prob, const uint8_t *frames_u8, const float 
     if (seg_u8) {
 #define X(k)                                                                                                                       \
         if (prob->K == k) {                                                                                                        \
-            if (prob->dtype == VLG_F32) {                                                                                          \
-                const int64_t n = P * ((out_onehot && (k % 4) == 0) ? k / 4 : 1);                                                  \
-                ingest_seg_kernel<float, k><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, W, flip, seg_u8, out_label, out_seg_f32, \
-                                                                                         (float *)out_onehot, (WsHeader *)workspace); \
-            } else {                                                                                                               \
-                const int64_t n = P * ((out_onehot && (k % 8) == 0) ? k / 8 : 1);                                                  \
-                ingest_seg_kernel<__nv_bfloat16, k><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(                                  \
-                    P, W, flip, seg_u8, out_label, out_seg_f32, (__nv_bfloat16 *)out_onehot, (WsHeader *)workspace);               \
-            }                                                                                                                      \
-            return check_launch("ingest_seg_kernel");                                                                             \
+            if (prob->dtype == VLG_F32) return launch_ingest_seg<float, k>(P, W, flip, seg_u8, out_label, out_seg_f32, out_onehot, workspace, st); \
+            return launch_ingest_seg<__nv_bfloat16, k>(P, W, flip, seg_u8, out_label, out_seg_f32, out_onehot, workspace, st);     \
         }
         VLG_FOR_EACH_K(X)
 #undef X

@@ -62,36 +62,64 @@ __global__ void __launch_bounds__(256) ingest_frames_px_kernel(IngestNorm nm, in
 }
 
 // uint8 class map [N,H,W] -> any of: int64 labels (seg3.long()), float32 class ids (seg1.float()), one-hot layout
-// [N,H,W,K] of type T.  One thread per 16-byte chunk of the one-hot output (a warp writes 512 contiguous bytes);
-// chunk 0 of a pixel also writes its label / class id.  Without a one-hot output: one thread per pixel.
-template <typename T, int K>
+// [N,H,W,K] of type T.  VEC (K * sizeof(T) a multiple of 16): warp-per-32-pixels, see below (the first version -- one
+// thread per 16-byte chunk, 64-bit indices divided by run-time values -- was issue-bound: 62 us for the 168 MB of a C2
+// one-hot layout).  Otherwise: one thread per pixel.
+template <typename T, int K, bool VEC>
 __global__ void __launch_bounds__(256) ingest_seg_kernel(int64_t P, int W, int flip, const uint8_t *__restrict__ seg, int64_t *__restrict__ out_label,
                                                          float *__restrict__ out_f32, T *__restrict__ out_onehot, WsHeader *hdr_or_null) {
-    constexpr int EPC = 16 / (int)sizeof(T);
-    constexpr bool kVec = (K % EPC) == 0;
-    const int CPP = (out_onehot && kVec) ? K / EPC : 1;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P * CPP) return;
-    const int64_t px = i / CPP;                       // OUTPUT pixel
-    const int chunk = (int)(i - px * CPP);
-    const int64_t row = px / W;
-    const int x = (int)(px - row * W);
-    const int l = (int)__ldg(seg + row * W + (flip ? W - 1 - x : x));
-    if (chunk == 0) {
+    if constexpr (VEC) {
+        // One WARP per 32 consecutive output pixels: every lane reads ONE class id, then the warp writes the 32 * CPP
+        // 16-byte chunks of those pixels in CPP fully coalesced rounds; chunk e of the run belongs to pixel e / CPP, whose
+        // class id comes from that lane by shuffle (all divisions by compile-time constants on values < 32 * CPP).
+        constexpr int EPC = 16 / (int)sizeof(T), CPP = K / EPC;
+        static_assert(K % EPC == 0, "vector path needs whole 16-byte chunks");
+        const unsigned lane = threadIdx.x & 31;
+        const int64_t px0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+        if (px0 >= P) return;                                             // warp-uniform
+        const unsigned px = (unsigned)px0 + lane;                         // N*H*W < 2^31
+        int l = 0;
+        if (px < (uint64_t)P) {
+            unsigned sp = px;
+            if (flip) {
+                const unsigned row = px / (unsigned)W, x = px - row * (unsigned)W;
+                sp = row * (unsigned)W + ((unsigned)W - 1u - x);
+            }
+            l = (int)__ldg(seg + sp);
+            if (out_label) out_label[px] = (int64_t)l;
+            if (out_f32) out_f32[px] = (float)l;
+            if (l >= K && hdr_or_null) atomicOr(&hdr_or_null->status, VLG_STATUS_BAD_LABEL);
+        }
+        const int npx = (int)min((int64_t)32, P - px0);
+        uint4 *dst = reinterpret_cast<uint4 *>(out_onehot) + px0 * CPP;
+#pragma unroll
+        for (int it = 0; it < CPP; ++it) {
+            const int e = it * 32 + (int)lane, q = e / CPP, chunk = e - q * CPP;
+            const int lq = __shfl_sync(0xffffffffu, l, q);
+            if (q < npx) {
+                uint4 r = make_uint4(0u, 0u, 0u, 0u);
+                T *v = reinterpret_cast<T *>(&r);
+                const int rel = lq - chunk * EPC;
+                if (rel >= 0 && rel < EPC) v[rel] = from_f<T>(1.0f);
+                dst[e] = r;
+            }
+        }
+    } else {
+        const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= P) return;
+        const unsigned px = (unsigned)i;
+        unsigned sp = px;
+        if (flip) {
+            const unsigned row = px / (unsigned)W, x = px - row * (unsigned)W;
+            sp = row * (unsigned)W + ((unsigned)W - 1u - x);
+        }
+        const int l = (int)__ldg(seg + sp);
         if (out_label) out_label[px] = (int64_t)l;
         if (out_f32) out_f32[px] = (float)l;
         if (l >= K && out_onehot && hdr_or_null) atomicOr(&hdr_or_null->status, VLG_STATUS_BAD_LABEL);
-    }
-    if (out_onehot) {
-        if constexpr (kVec) {
-            uint4 r = make_uint4(0u, 0u, 0u, 0u);
-            T *e = reinterpret_cast<T *>(&r);
-            const int rel = l - chunk * EPC;
-            if (rel >= 0 && rel < EPC) e[rel] = from_f<T>(1.0f);
-            reinterpret_cast<uint4 *>(out_onehot + px * K)[chunk] = r;
-        } else {
+        if (out_onehot) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) out_onehot[px * K + k] = from_f<T>(l == k ? 1.0f : 0.0f);
+            for (int k = 0; k < K; ++k) out_onehot[(int64_t)px * K + k] = from_f<T>(l == k ? 1.0f : 0.0f);
         }
     }
 }
