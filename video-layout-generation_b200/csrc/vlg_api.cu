@@ -358,27 +358,47 @@ __global__ void __launch_bounds__(256) colorize_kernel(int64_t P, const T *__res
     store_px<T, 3>(out_rgb + i * 3, rgb);
 }
 
-// One-hot layout encoding (src/models/net_utils.py:14-24): one thread per 16-byte chunk of the output,
-// so a warp writes 512 contiguous bytes; the class id of a chunk's pixel is read once per chunk.
+// One-hot layout encoding (src/models/net_utils.py:14-24).  Whole 16-byte chunks per pixel: one WARP per 32 consecutive
+// pixels -- every lane reads one class id, the 32 * CPP chunks leave in CPP coalesced rounds, the id of a chunk's pixel
+// comes by shuffle (same scheme as ingest_seg_kernel: a thread per chunk spent its time dividing 64-bit indices).
+// Otherwise one thread per pixel.
 template <typename T, int K>
 __global__ void __launch_bounds__(256) one_hot_kernel(int64_t P, const int64_t *__restrict__ lab_i, const float *__restrict__ lab_f,
                                                       T *__restrict__ out, WsHeader *hdr_or_null) {
     constexpr int EPC = 16 / (int)sizeof(T);                    // elements per 16-byte chunk
     constexpr bool kVec = (K % EPC) == 0;
-    constexpr int CPP = kVec ? K / EPC : 1;                     // chunks per pixel (1: scalar fallback, one thread per pixel)
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P * CPP) return;
-    const int64_t px = i / CPP;
-    const int chunk = (int)(i - px * CPP);
-    const int64_t l = lab_i ? __ldg(lab_i + px) : (int64_t)__ldg(lab_f + px);   // .long() truncation
-    if ((l < 0 || l >= K) && hdr_or_null && chunk == 0) atomicOr(&hdr_or_null->status, VLG_STATUS_BAD_LABEL);
     if constexpr (kVec) {
-        uint4 r = make_uint4(0u, 0u, 0u, 0u);
-        T *e = reinterpret_cast<T *>(&r);
-        const int64_t rel = l - (int64_t)chunk * EPC;
-        if (rel >= 0 && rel < EPC) e[rel] = from_f<T>(1.0f);
-        reinterpret_cast<uint4 *>(out + px * K)[chunk] = r;
+        constexpr int CPP = K / EPC;                            // chunks per pixel
+        const unsigned lane = threadIdx.x & 31;
+        const int64_t px0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+        if (px0 >= P) return;                                   // warp-uniform
+        const int64_t px = px0 + lane;
+        int l = -1;
+        if (px < P) {
+            const int64_t l64 = lab_i ? __ldg(lab_i + px) : (int64_t)__ldg(lab_f + px);   // .long() truncation
+            const bool bad = l64 < 0 || l64 >= K;
+            if (bad && hdr_or_null) atomicOr(&hdr_or_null->status, VLG_STATUS_BAD_LABEL);
+            l = bad ? -1 : (int)l64;                            // out-of-range ids encode as an all-zero pixel
+        }
+        const int npx = (int)min((int64_t)32, P - px0);
+        uint4 *dst = reinterpret_cast<uint4 *>(out) + px0 * CPP;
+#pragma unroll
+        for (int it = 0; it < CPP; ++it) {
+            const int e = it * 32 + (int)lane, q = e / CPP, chunk = e - q * CPP;
+            const int lq = __shfl_sync(0xffffffffu, l, q);
+            if (q < npx) {
+                uint4 r = make_uint4(0u, 0u, 0u, 0u);
+                T *v = reinterpret_cast<T *>(&r);
+                const int rel = lq - chunk * EPC;
+                if (lq >= 0 && rel >= 0 && rel < EPC) v[rel] = from_f<T>(1.0f);
+                dst[e] = r;
+            }
+        }
     } else {
+        const int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (px >= P) return;
+        const int64_t l = lab_i ? __ldg(lab_i + px) : (int64_t)__ldg(lab_f + px);
+        if ((l < 0 || l >= K) && hdr_or_null) atomicOr(&hdr_or_null->status, VLG_STATUS_BAD_LABEL);
 #pragma unroll
         for (int k = 0; k < K; ++k) out[px * K + k] = from_f<T>(l == k ? 1.0f : 0.0f);
     }
@@ -387,7 +407,7 @@ __global__ void __launch_bounds__(256) one_hot_kernel(int64_t P, const int64_t *
 template <typename T, int K>
 static int launch_one_hot(int64_t P, const int64_t *lab_i, const float *lab_f, void *out, void *workspace, cudaStream_t st) {
     constexpr int EPC = 16 / (int)sizeof(T);
-    const int64_t n = P * ((K % EPC) == 0 ? K / EPC : 1);
+    const int64_t n = (K % EPC) == 0 ? ((P + 31) / 32) * 32 : P;     // a warp per 32 pixels / a thread per pixel
     one_hot_kernel<T, K><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, lab_i, lab_f, (T *)out, (WsHeader *)workspace);
     return check_launch("one_hot_kernel");
 }
