@@ -291,8 +291,10 @@ __global__ void __launch_bounds__(256) warp_fwd_labels_kernel(CoordCfg cc, int64
                                                               int64_t *out_label) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    const int64_t n = i / HW, rem = i - n * HW;
-    const int y = (int)(rem / cc.W), x = (int)(rem - (int64_t)y * cc.W);
+    // N*H*W < 2^31 (check_problem): 32-bit divisions (a 64-bit division by a run-time value costs ~60 instructions)
+    const unsigned nu = (unsigned)i / (unsigned)HW, rem = (unsigned)i - nu * (unsigned)HW;
+    const int64_t n = nu;
+    const int y = (int)(rem / (unsigned)cc.W), x = (int)(rem - (unsigned)y * (unsigned)cc.W);
     const Taps t = make_taps(cc, __ldg(coords + i), y, x);
     if (src_rgb && out_rgb) {
         float a[3];
@@ -424,8 +426,9 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(CoordCfg cc, int64_t P, i
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < P;
     const int64_t ic = live ? i : P - 1;
-    const int64_t n = ic / HW, rem = ic - n * HW;
-    const int y = (int)(rem / cc.W), x = (int)(rem - (int64_t)y * cc.W);
+    const unsigned nu = (unsigned)ic / (unsigned)HW, rem = (unsigned)ic - nu * (unsigned)HW;   // N*H*W < 2^31: 32-bit divisions
+    const int64_t n = nu;
+    const int y = (int)(rem / (unsigned)cc.W), x = (int)(rem - (unsigned)y * (unsigned)cc.W);
     const Taps t = make_taps(cc, __ldg(coords + ic), y, x);
     if (dbg && live) dbg[i] = make_int2((int)t.fx0, (int)t.fy0);
     if (src_rgb && out_rgb && live) {

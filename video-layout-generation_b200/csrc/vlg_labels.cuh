@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(kLabThreads) lab_pix_kernel(const LabParams p)
     const int64_t per_cta = (p.P + gridDim.x - 1) / gridDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * per_cta, i1 = min(p.P, i0 + per_cta);
     for (int64_t i = i0 + threadIdx.x; i < i1; i += kLabThreads) {
-        const int64_t n = i / p.HW, rem = i - n * p.HW;
-        const int y = (int)(rem / W), x = (int)(rem - (int64_t)y * W);
+        // N*H*W < 2^31 (check_problem): 32-bit divisions (a 64-bit division by a run-time value costs ~60 instructions)
+        const unsigned nu = (unsigned)i / (unsigned)p.HW, rem = (unsigned)i - nu * (unsigned)p.HW;
+        const int64_t n = nu;
+        const int y = (int)(rem / (unsigned)W), x = (int)(rem - (unsigned)y * (unsigned)W);
         const float2 f = __ldg(p.coords + i);
         const Taps t = make_taps(cc, f, y, x);
         const int64_t lb = __ldg(p.tgt_label + i);

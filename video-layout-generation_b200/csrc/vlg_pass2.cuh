@@ -450,8 +450,10 @@ __global__ void __launch_bounds__(256) tap_records_kernel(CoordCfg cc, int64_t P
                                                           const float2 *__restrict__ coords, uint32_t *rec_code, float2 *rec_frac) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    const int64_t n = i / HW, rem = i - n * HW;
-    const int y = (int)(rem / cc.W), x = (int)(rem - (int64_t)y * cc.W);
+    // N*H*W < 2^31 (check_problem): 32-bit divisions (a 64-bit division by a run-time value costs ~60 instructions)
+    const unsigned nu = (unsigned)i / (unsigned)HW, rem = (unsigned)i - nu * (unsigned)HW;
+    const int64_t n = nu;
+    const int y = (int)(rem / (unsigned)cc.W), x = (int)(rem - (unsigned)y * (unsigned)cc.W);
     const Taps t = make_taps(cc, __ldg(coords + i), y, x);
     const int64_t ro = (n * cc.H + y) * pitch + x;
     rec_code[ro] = tap_cell_code(cc, t, y, x);
